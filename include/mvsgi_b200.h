@@ -1,0 +1,210 @@
+/*
+ * mvsgi_b200.h — C ABI of libmvsgi_b200.so
+ *
+ * B200-native (sm_100a) replacement for the spherical-sweep / cost-volume /
+ * soft-argmin hot path of castacks/mvs_gi.  Plain pointers and sizes only: no
+ * torch types cross this boundary.  Every entry point cites the reference
+ * interface it replaces (paths relative to the reference checkout).
+ *
+ * Ownership: the caller allocates every input, output and workspace buffer.
+ * The library never allocates, frees or retains device memory; pointers are
+ * borrowed for the duration of the enqueue.  Calibration (MvsgiRig) is read
+ * from HOST memory at enqueue time and passed to the kernels by value.
+ *
+ * Threading/streams: re-entrant, no global mutable state.  Work is enqueued on
+ * the stream that is passed in (a cudaStream_t cast to void*); no call
+ * synchronises the device, so all of them are safe under CUDA-graph capture.
+ *
+ * Errors: 0 = enqueued.  Negative = MVSGI_E_* argument error (nothing was
+ * enqueued).  Positive = cudaError_t from the launch.  No exceptions, no exit.
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef MVSGI_B200_H_
+#define MVSGI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVSGI_ABI_VERSION 3
+#define MVSGI_MAX_CAMS 4
+#define MVSGI_MAX_CANDS 64
+
+/* ---- error codes ------------------------------------------------------- */
+#define MVSGI_OK 0
+#define MVSGI_E_NULL (-1)        /* required pointer is NULL                 */
+#define MVSGI_E_SHAPE (-2)       /* a size is <= 0 or exceeds a limit        */
+#define MVSGI_E_STRIDE (-3)      /* unsupported stride / alignment           */
+#define MVSGI_E_UNSUPPORTED (-4) /* enum value / combination not implemented */
+#define MVSGI_E_WORKSPACE (-5)   /* workspace too small or misaligned        */
+#define MVSGI_E_VERSION (-6)     /* struct_size does not match this ABI      */
+
+/* ---- enums ------------------------------------------------------------- */
+/* Camera models of dsta_mvs/mvs_utils/camera_models.py that the sweep can
+ * project into (Equirectangular :577, DoubleSphere :388, LinearSphere :1427). */
+enum { MVSGI_CAM_EQUIRECT = 0, MVSGI_CAM_DOUBLE_SPHERE = 1, MVSGI_CAM_LINEAR_SPHERE = 2 };
+/* Where the sampling grid comes from. */
+enum {
+  MVSGI_GRID_SUPPLIED = 0, /* caller passes grids/grid_masks (reference interface) */
+  MVSGI_GRID_PROJECT = 1   /* evaluated in-kernel from MvsgiRig                    */
+};
+/* Cross-view aggregation = which cv_builder (configs/cv_builder/{std,concat}_cvbuilder.yaml). */
+enum {
+  MVSGI_AGG_STD = 0,   /* SphericalSweepStdMasked.sweep  spherical_sweep_avg.py:38-136 */
+  MVSGI_AGG_CONCAT = 1 /* SphericalSweep.sweep           spherical_sweep.py:38-68      */
+};
+/* Element type of the masks tensor. */
+enum { MVSGI_MASK_F32 = 0, MVSGI_MASK_U8 = 1 };
+/* flags for MvsgiSweepArgs.flags */
+#define MVSGI_FLAG_FEATS_BF16 1u /* stage features as bf16 (fp32 accumulate); stated-tolerance mode */
+
+/* ---- calibration ------------------------------------------------------- */
+/* One camera the sweep projects into.  rot/trans are the INVERSE pose
+ * (R^T, -R^T t) of T_cv_cam, i.e. what FTensor.inverse()
+ * (dsta_mvs/mvs_utils/ftensor/ftensor.py:454-476) hands to
+ * transform_3D_points_torch (dsta_mvs/support/dataset/torch_cuda_sweep.py:385-408).
+ * All scalars are float32 exactly as the reference casts them.
+ *   p[] by model:
+ *   EQUIRECT       : lon0, lon1, lon_span_pixel, lat0, lat_range(=lat1-lat0)
+ *                    (camera_models.py:640-652, :741-764)
+ *   DOUBLE_SPHERE  : xi, alpha, one_minus_alpha, fx, fy, cx, cy, neg_w2, half_fov
+ *                    (camera_models.py:492-529, :400-408)
+ *   LINEAR_SPHERE  : fov_rad            (camera_models.py:1506-1548)
+ */
+typedef struct MvsgiCamera {
+  int32_t model;
+  int32_t width;  /* ss.W used by the normalisation */
+  int32_t height; /* ss.H */
+  int32_t reserved;
+  float rot[9];   /* row-major 3x3 */
+  float trans[3];
+  float p[12];
+} MvsgiCamera;
+
+/* The cost-volume camera (always Equirectangular in the reference:
+ * configs/dataset/cam_model_cv.yaml) + rig + candidate distances.
+ * Rays follow Equirectangular.pixel_2_ray (camera_models.py:680-720) scaled by
+ * RayMaker.make_rays_from_candidates (torch_cuda_sweep.py:186-215). */
+typedef struct MvsgiRig {
+  int32_t num_cams;
+  int32_t num_cands;
+  int32_t cv_width;
+  int32_t cv_height;
+  float cv_lon0;
+  float cv_lon_span_pixel;
+  float cv_lat0;
+  float cv_lat_range;
+  MvsgiCamera cams[MVSGI_MAX_CAMS];
+  float dist[MVSGI_MAX_CANDS]; /* FixedDistLabelTable.dist()  dist_label_table.py:104-122 */
+} MvsgiRig;
+
+/* ---- sweep + aggregation ----------------------------------------------- */
+/* Replaces SphericalSweepStdMasked.sweep(feats, grids, grid_masks, masks)
+ * (spherical_sweep_avg.py:38-136) and SphericalSweep.sweep(feats, grids, masks)
+ * (spherical_sweep.py:38-68), including their sampler bilinear_grid_sample
+ * (dsta_mvs/model/backports/backports.py:11-86).
+ * Strides are in ELEMENTS of the tensor's own dtype.  A batch stride of 0 on
+ * masks / grids / grid_masks means "shared by all frames" and lets the kernel
+ * evaluate the geometry once per tile instead of once per frame. */
+typedef struct MvsgiSweepArgs {
+  uint32_t struct_size; /* = sizeof(MvsgiSweepArgs) */
+  int32_t aggregate;    /* MVSGI_AGG_*  */
+  int32_t grid_mode;    /* MVSGI_GRID_* */
+  uint32_t flags;
+  int32_t batch, num_cams, feat_chs, num_cands;
+  int32_t feat_h, feat_w; /* Hi, Wi of feats            */
+  int32_t mask_h, mask_w; /* H, W of masks (std only)   */
+  int32_t out_h, out_w;   /* Ho, Wo of the cost volume  */
+
+  const float* feats;      /* [B, CAM, C, Hf, Wf] fp32 */
+  int64_t feats_stride[5]; /* B, CAM, C, H, W */
+
+  const void* masks;       /* [B, CAM, 1, Hm, Wm] fp32 0/1 (or u8); NULL for concat */
+  int32_t masks_dtype;     /* MVSGI_MASK_* */
+  int32_t reserved0;
+  int64_t masks_stride[4]; /* B, CAM, H, W */
+
+  const float* grids;      /* [B, CAM, D, Ho, Wo, 2]; last dim contiguous; NULL in PROJECT mode */
+  int64_t grids_stride[5]; /* B, CAM, D, H, W */
+  const uint8_t* grid_masks; /* [B, CAM, D, Ho, Wo, 1] bool; NULL in PROJECT mode / concat */
+  int64_t grid_masks_stride[5];
+
+  const MvsgiRig* rig;     /* HOST pointer; required in PROJECT mode */
+
+  float* vol;              /* [B, Cout, D, Ho, Wo] contiguous; Cout = C (std) or CAM*C (concat) */
+  uint8_t* valid_out;      /* optional [B, D, Ho, Wo]: 1 where >1 camera valid (std); may be NULL */
+
+  void* workspace;         /* >= mvsgi_sweep_workspace_bytes(args), 256-byte aligned */
+  int64_t workspace_bytes;
+} MvsgiSweepArgs;
+
+/* Scratch the sweep needs for this problem (channels-last staging of feats when
+ * they are not already channels-last, bit-packed masks).  Negative = error. */
+int64_t mvsgi_sweep_workspace_bytes(const MvsgiSweepArgs* args);
+
+/* Enqueue staging (if needed) + the fused sweep/aggregate kernel. */
+int mvsgi_sweep_f32(const MvsgiSweepArgs* args, void* cuda_stream);
+
+/* Number of kernels the last-described problem launches (for gpu_launches
+ * accounting in bench.py): staging transposes + mask pack + sweep. */
+int mvsgi_sweep_launch_count(const MvsgiSweepArgs* args);
+
+/* ---- grid evaluation only (debug / oracle hand-off) --------------------- */
+/* Replaces the CPU precompute MultiViewCameraModelDataset.create_grids_from_rays
+ * (dsta_mvs/support/dataset/multi_view_camera_model_dataset.py:530-557,474-518):
+ * writes the kernel's own grids so that the oracle can consume exactly what the
+ * fused kernel samples with. */
+typedef struct MvsgiProjectArgs {
+  uint32_t struct_size;
+  int32_t reserved;
+  const MvsgiRig* rig;  /* HOST pointer */
+  float* grids;         /* [CAM, D, Ho, Wo, 2] contiguous */
+  uint8_t* grid_masks;  /* [CAM, D, Ho, Wo] contiguous (1 = valid) */
+} MvsgiProjectArgs;
+int mvsgi_project_only_f32(const MvsgiProjectArgs* args, void* cuda_stream);
+
+/* ---- mask packing -------------------------------------------------------- */
+/* Packs masks (>0 -> 1) into the padded bit layout the sweep samples:
+ * per (n) image: (Hm+2) rows x pitch_words uint32, bit (x+1) of row (y+1).
+ * flags_out[0] gets bit0 set if any mask value is negative or NaN (then the
+ * "bilinear(mask) > 0" test of spherical_sweep_avg.py:92-96 is not equivalent
+ * to the packed test and the caller should reject the input). */
+int32_t mvsgi_mask_pitch_words(int32_t mask_w);
+int mvsgi_pack_masks(const void* masks, int32_t masks_dtype, int32_t n_images, int64_t image_stride_outer,
+                     int32_t n_inner, int64_t image_stride_inner, int64_t stride_h, int64_t stride_w,
+                     int32_t mask_h, int32_t mask_w, uint32_t* bits_out, int32_t* flags_out, void* cuda_stream);
+
+/* ---- soft-argmin distance regression ------------------------------------ */
+/* Replaces DistanceRegressorWithFixedCandidates.forward
+ * (dsta_mvs/model/distance_regressor/distance_regressor.py:51-80):
+ * costs[:,0] -> optional bilinear upsample (F.interpolate, align_corners=False)
+ * -> softmax over D -> sum_d p_d * inv_dist_idx_d. */
+typedef struct MvsgiSoftArgminArgs {
+  uint32_t struct_size;
+  uint32_t flags;
+  int32_t batch, num_cands;
+  int32_t in_h, in_w;
+  int32_t out_h, out_w;  /* == in_h,in_w when no interpolation */
+  float src_scale_h;     /* source-index scale of F.interpolate = 1/scale_factor */
+  float src_scale_w;
+  const float* costs;      /* element (b, d, y, x) of costs[:,0] */
+  int64_t costs_stride[4]; /* B, D, H, W */
+  const float* inv_dist_idx; /* device [D] = bf / dist  (distance_regressor.py:29-32) */
+  float* inv_dist;         /* [B, 1, out_h, out_w] contiguous */
+  float* norm_costs;       /* [B, D, out_h, out_w] contiguous, or NULL (inference) */
+  int32_t* argmax;         /* [B, out_h, out_w] first-max candidate index, or NULL */
+} MvsgiSoftArgminArgs;
+int mvsgi_softargmin_f32(const MvsgiSoftArgminArgs* args, void* cuda_stream);
+
+/* ---- misc ---------------------------------------------------------------- */
+const char* mvsgi_strerror(int code);
+int mvsgi_abi_version(void);
+/* Kernel launches issued through this library by the calling process so far. */
+int64_t mvsgi_launch_counter(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSGI_B200_H_ */

@@ -1,0 +1,171 @@
+"""ctypes mirror of include/mvsgi_b200.h and the loader for libmvsgi_b200.so.
+
+The product path has exactly one implementation: the CUDA library.  If the
+library is missing this module raises at first use — there is no CPU or eager
+PyTorch fallback (north_star: "no CPU fallback").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+ABI_VERSION = 3
+MAX_CAMS = 4
+MAX_CANDS = 64
+
+CAM_EQUIRECT, CAM_DOUBLE_SPHERE, CAM_LINEAR_SPHERE = 0, 1, 2
+GRID_SUPPLIED, GRID_PROJECT = 0, 1
+AGG_STD, AGG_CONCAT = 0, 1
+MASK_F32, MASK_U8 = 0, 1
+FLAG_FEATS_BF16 = 1
+
+LIB_NAME = "libmvsgi_b200.so"
+_PKG_DIR = Path(__file__).resolve().parent
+
+
+class MvsgiCamera(C.Structure):
+    _fields_ = [
+        ("model", C.c_int32),
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("reserved", C.c_int32),
+        ("rot", C.c_float * 9),
+        ("trans", C.c_float * 3),
+        ("p", C.c_float * 12),
+    ]
+
+
+class MvsgiRig(C.Structure):
+    _fields_ = [
+        ("num_cams", C.c_int32),
+        ("num_cands", C.c_int32),
+        ("cv_width", C.c_int32),
+        ("cv_height", C.c_int32),
+        ("cv_lon0", C.c_float),
+        ("cv_lon_span_pixel", C.c_float),
+        ("cv_lat0", C.c_float),
+        ("cv_lat_range", C.c_float),
+        ("cams", MvsgiCamera * MAX_CAMS),
+        ("dist", C.c_float * MAX_CANDS),
+    ]
+
+
+class MvsgiSweepArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("aggregate", C.c_int32),
+        ("grid_mode", C.c_int32),
+        ("flags", C.c_uint32),
+        ("batch", C.c_int32),
+        ("num_cams", C.c_int32),
+        ("feat_chs", C.c_int32),
+        ("num_cands", C.c_int32),
+        ("feat_h", C.c_int32),
+        ("feat_w", C.c_int32),
+        ("mask_h", C.c_int32),
+        ("mask_w", C.c_int32),
+        ("out_h", C.c_int32),
+        ("out_w", C.c_int32),
+        ("feats", C.c_void_p),
+        ("feats_stride", C.c_int64 * 5),
+        ("masks", C.c_void_p),
+        ("masks_dtype", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("masks_stride", C.c_int64 * 4),
+        ("grids", C.c_void_p),
+        ("grids_stride", C.c_int64 * 5),
+        ("grid_masks", C.c_void_p),
+        ("grid_masks_stride", C.c_int64 * 5),
+        ("rig", C.POINTER(MvsgiRig)),
+        ("vol", C.c_void_p),
+        ("valid_out", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
+    ]
+
+
+class MvsgiProjectArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("reserved", C.c_int32),
+        ("rig", C.POINTER(MvsgiRig)),
+        ("grids", C.c_void_p),
+        ("grid_masks", C.c_void_p),
+    ]
+
+
+class MvsgiSoftArgminArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("batch", C.c_int32),
+        ("num_cands", C.c_int32),
+        ("in_h", C.c_int32),
+        ("in_w", C.c_int32),
+        ("out_h", C.c_int32),
+        ("out_w", C.c_int32),
+        ("src_scale_h", C.c_float),
+        ("src_scale_w", C.c_float),
+        ("costs", C.c_void_p),
+        ("costs_stride", C.c_int64 * 4),
+        ("inv_dist_idx", C.c_void_p),
+        ("inv_dist", C.c_void_p),
+        ("norm_costs", C.c_void_p),
+        ("argmax", C.c_void_p),
+    ]
+
+
+# Every symbol include/mvsgi_b200.h declares: name -> (restype, argtypes).
+EXPORTS = {
+    "mvsgi_sweep_workspace_bytes": (C.c_int64, [C.POINTER(MvsgiSweepArgs)]),
+    "mvsgi_sweep_f32": (C.c_int, [C.POINTER(MvsgiSweepArgs), C.c_void_p]),
+    "mvsgi_sweep_launch_count": (C.c_int, [C.POINTER(MvsgiSweepArgs)]),
+    "mvsgi_project_only_f32": (C.c_int, [C.POINTER(MvsgiProjectArgs), C.c_void_p]),
+    "mvsgi_mask_pitch_words": (C.c_int32, [C.c_int32]),
+    "mvsgi_pack_masks": (
+        C.c_int,
+        [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "mvsgi_softargmin_f32": (C.c_int, [C.POINTER(MvsgiSoftArgminArgs), C.c_void_p]),
+    "mvsgi_strerror": (C.c_char_p, [C.c_int]),
+    "mvsgi_abi_version": (C.c_int, []),
+    "mvsgi_launch_counter": (C.c_int64, []),
+}
+
+_lib = None
+
+
+def library_path() -> Path:
+    override = os.environ.get("MVSGI_B200_LIB")
+    return Path(override) if override else _PKG_DIR / LIB_NAME
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree CUDA library; raise loudly when it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise RuntimeError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"(or `make -C mvs_gi_b200/csrc`). mvs_gi_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(str(path))
+    for name, (restype, argtypes) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the .so disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    got = lib.mvsgi_abi_version()
+    if got != ABI_VERSION:
+        raise RuntimeError(f"{path}: ABI version {got}, python side expects {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load_library().mvsgi_strerror(code)
+        raise RuntimeError(f"{what} failed: {msg.decode() if msg else code} (code {code})")

@@ -1,0 +1,392 @@
+/*
+ * mvsgi_oracle.c — CPU restatement of the mvs_gi sweep / cost-volume /
+ * soft-argmin path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs may load this library, and only as the checker or
+ * the timed CPU baseline.  Nothing under mvs_gi_b200/ imports it.
+ *
+ * Parity status: the reference has no golden vectors or unit tests for this
+ * path, so this restatement is pinned against outputs of the
+ * reference's own modules, run from /root/reference by oracle/gen_golden.py
+ * and committed under tests/golden/ (tests/test_oracle_golden.py).
+ *
+ * Everything is fp32 evaluated in the reference's operation order; build with
+ * -ffp-contract=off so the compiler does not fuse multiply-adds the reference
+ * (eager PyTorch, one rounding per op) does not have.  The one place PyTorch
+ * itself fuses (the bilinear upsample of F.interpolate) uses fmaf explicitly.
+ *
+ * Paths below are relative to the reference checkout.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/mvsgi_b200.h" /* MvsgiRig / MvsgiCamera POD only */
+
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* dsta_mvs/model/backports/backports.py:11-86  bilinear_grid_sample           */
+/* (zero padding, align_corners=False).  One sample point, all channels.      */
+/* im is [C, H, W] with element strides (sc, sy, sx).                         */
+typedef struct {
+  long x0c, x1c, y0c, y1c; /* indices into the zero-padded image, clamped (:65-72) */
+  float wa, wb, wc, wd;    /* :52-55 */
+} orc_taps;
+
+static inline void orc_make_taps(float gx, float gy, int H, int W, orc_taps* t) {
+  /* :41-42 (align_corners=False):  x = ((x + 1) * w - 1) / 2 */
+  float x = ((gx + 1.0f) * (float)W - 1.0f) / 2.0f;
+  float y = ((gy + 1.0f) * (float)H - 1.0f) / 2.0f;
+  /* :47-50 */
+  float fx0 = floorf(x), fy0 = floorf(y);
+  long x0 = (long)fx0, y0 = (long)fy0;
+  long x1 = x0 + 1, y1 = y0 + 1;
+  /* :52-55 — long - float promotes the long to float32 */
+  float dx1 = (float)x1 - x, dx0 = x - (float)x0;
+  float dy1 = (float)y1 - y, dy0 = y - (float)y0;
+  t->wa = dx1 * dy1;
+  t->wb = dx1 * dy0;
+  t->wc = dx0 * dy1;
+  t->wd = dx0 * dy0;
+  /* :58-72 pad by one, shift, clamp into the padded extent */
+  long pw = W + 2, ph = H + 2;
+  x0 += 1; x1 += 1; y0 += 1; y1 += 1;
+  if (x0 < 0) x0 = 0; if (x0 > pw - 1) x0 = pw - 1;
+  if (x1 < 0) x1 = 0; if (x1 > pw - 1) x1 = pw - 1;
+  if (y0 < 0) y0 = 0; if (y0 > ph - 1) y0 = ph - 1;
+  if (y1 < 0) y1 = 0; if (y1 > ph - 1) y1 = ph - 1;
+  t->x0c = x0; t->x1c = x1; t->y0c = y0; t->y1c = y1;
+}
+
+/* value of the zero-padded image at padded coords (:58, :76-84) */
+static inline float orc_padded(const float* im, int H, int W, int64_t sy, int64_t sx, long yp, long xp) {
+  if (yp < 1 || yp > H || xp < 1 || xp > W) return 0.0f;
+  return im[(yp - 1) * sy + (xp - 1) * sx];
+}
+
+static inline float orc_sample1(const float* im, int H, int W, int64_t sy, int64_t sx, const orc_taps* t) {
+  float Ia = orc_padded(im, H, W, sy, sx, t->y0c, t->x0c);
+  float Ib = orc_padded(im, H, W, sy, sx, t->y1c, t->x0c);
+  float Ic = orc_padded(im, H, W, sy, sx, t->y0c, t->x1c);
+  float Id = orc_padded(im, H, W, sy, sx, t->y1c, t->x1c);
+  /* :86  Ia * wa + Ib * wb + Ic * wc + Id * wd, left to right */
+  return ((Ia * t->wa + Ib * t->wb) + Ic * t->wc) + Id * t->wd;
+}
+
+/* Stand-alone sampler: im [N,C,H,W] contiguous, grid [N,Hg,Wg,2], out [N,C,Hg,Wg]. */
+void orc_bilinear_grid_sample(const float* im, int N, int C, int H, int W, const float* grid, int Hg, int Wg,
+                              float* out) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int n = 0; n < N; ++n)
+    for (int i = 0; i < Hg * Wg; ++i) {
+      orc_taps t;
+      const float* g = grid + ((int64_t)n * Hg * Wg + i) * 2;
+      orc_make_taps(g[0], g[1], H, W, &t);
+      for (int c = 0; c < C; ++c)
+        out[((int64_t)n * C + c) * Hg * Wg + i] = orc_sample1(im + ((int64_t)n * C + c) * H * W, H, W, W, 1, &t);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* dsta_mvs/model/cost_volume_builder/spherical_sweep_avg.py:38-136           */
+/* SphericalSweepStdMasked.sweep.  All tensors contiguous fp32 / uint8:        */
+/*   feats [B,CAM,C,Hf,Wf]  masks [B,CAM,1,Hm,Wm]  grids [B,CAM,D,Ho,Wo,2]     */
+/*   grid_masks [B,CAM,D,Ho,Wo]  ->  vol [B,C,D,Ho,Wo], valid [B,D,Ho,Wo]      */
+/* A batch stride of 0 may be passed for masks/grids/grid_masks (shared).     */
+void orc_sweep_std(const float* feats, const float* masks, const float* grids, const uint8_t* grid_masks, int B,
+                   int CAM, int C, int D, int Hf, int Wf, int Hm, int Wm, int Ho, int Wo, int64_t masks_bstride,
+                   int64_t grids_bstride, int64_t gm_bstride, float* vol, uint8_t* valid_out) {
+  const int64_t HW = (int64_t)Ho * Wo;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < D; ++i) { /* the reference's `for i in range(X)` :59 */
+      float* f = (float*)malloc(sizeof(float) * (size_t)CAM * C);
+      for (int64_t px = 0; px < HW; ++px) {
+        int m[MVSGI_MAX_CAMS * 4];
+        float summed = 0.0f; /* :106 torch.sum(sampled_mask.to(float), dim=1) */
+        for (int cam = 0; cam < CAM; ++cam) {
+          const float* g = grids + b * grids_bstride + (((int64_t)cam * D + i) * HW + px) * 2;
+          orc_taps tf, tm;
+          /* :73-77 features sampled at feature resolution */
+          orc_make_taps(g[0], g[1], Hf, Wf, &tf);
+          for (int c = 0; c < C; ++c)
+            f[cam * C + c] = orc_sample1(feats + (((int64_t)b * CAM + cam) * C + c) * Hf * Wf, Hf, Wf, Wf, 1, &tf);
+          /* :92-96 masks sampled with the same normalised grid at mask resolution, > 0 */
+          orc_make_taps(g[0], g[1], Hm, Wm, &tm);
+          float sm = orc_sample1(masks + b * masks_bstride + (int64_t)cam * Hm * Wm, Hm, Wm, Wm, 1, &tm);
+          int mk = sm > 0.0f;
+          /* :60-62,:102 AND with the grid mask */
+          mk = mk && (grid_masks[b * gm_bstride + ((int64_t)cam * D + i) * HW + px] != 0);
+          m[cam] = mk;
+          summed += mk ? 1.0f : 0.0f;
+        }
+        int valid = summed > 1.0f;               /* :108 */
+        float cnt = valid ? summed : 1.0f;       /* :111 */
+        if (valid_out) valid_out[((int64_t)b * D + i) * HW + px] = (uint8_t)valid;
+        for (int c = 0; c < C; ++c) {
+          /* :114 avg = sum(sampled_feat * mask) / cam_count   (sequential over cams) */
+          float s = 0.0f;
+          for (int cam = 0; cam < CAM; ++cam) {
+            float term = f[cam * C + c] * (m[cam] ? 1.0f : 0.0f);
+            s = (cam == 0) ? term : s + term;
+          }
+          float avg = s / cnt;
+          /* :119-122 sampled_feat = where(mask, feat, avg); std2 = sum((f-avg)**2)/cnt */
+          float v = 0.0f;
+          for (int cam = 0; cam < CAM; ++cam) {
+            float fv = m[cam] ? f[cam * C + c] : avg;
+            float d = fv - avg;
+            float sq = d * d;
+            v = (cam == 0) ? sq : v + sq;
+          }
+          v = v / cnt;
+          /* :125 */
+          vol[(((int64_t)b * C + c) * D + i) * HW + px] = valid ? v : 0.0f;
+        }
+      }
+      free(f);
+    }
+}
+
+/* dsta_mvs/model/cost_volume_builder/spherical_sweep.py:38-68  SphericalSweep.sweep */
+/* vol[b, cam*C + c, d, h, w] = bilinear(feats[b,cam,c], grids[b,cam,d,h,w])  (:52-67) */
+void orc_sweep_concat(const float* feats, const float* grids, int B, int CAM, int C, int D, int Hf, int Wf, int Ho,
+                      int Wo, int64_t grids_bstride, float* vol) {
+  const int64_t HW = (int64_t)Ho * Wo;
+#pragma omp parallel for collapse(3) schedule(static)
+  for (int b = 0; b < B; ++b)
+    for (int cam = 0; cam < CAM; ++cam)
+      for (int i = 0; i < D; ++i)
+        for (int64_t px = 0; px < HW; ++px) {
+          const float* g = grids + b * grids_bstride + (((int64_t)cam * D + i) * HW + px) * 2;
+          orc_taps t;
+          orc_make_taps(g[0], g[1], Hf, Wf, &t);
+          for (int c = 0; c < C; ++c)
+            vol[((((int64_t)b * CAM + cam) * C + c) * D + i) * HW + px] =
+                orc_sample1(feats + (((int64_t)b * CAM + cam) * C + c) * Hf * Wf, Hf, Wf, Wf, 1, &t);
+        }
+}
+
+/* ------------------------------------------------------------------------- */
+/* dsta_mvs/model/distance_regressor/distance_regressor.py:51-80              */
+/* The upsample is PyTorch's F.interpolate(mode='bilinear', align_corners=    */
+/* False, scale_factor=s) — third-party arithmetic (torch, not pinned by the  */
+/* reference beyond NGC 22.11; restated from ATen UpSampleKernel.cpp):        */
+/*   src = fma(scale, dst+0.5, -0.5) clamped >= 0, i0=(int)src, i1=min(i0+1,n-1), */
+/*   l1 = src-i0, l0 = 1-l1,                                                  */
+/*   out = fma(ly0, fma(lx0,v00, lx1*v01), ly1*fma(lx0,v10, lx1*v11))         */
+/* The fma placement was determined empirically against torch 2.11 CPU        */
+/* (bit-exact on 2x16x80x320 random input; see oracle/gen_golden.py).         */
+static inline void orc_src_index(int dst, float scale, int n_in, int* i0, int* i1, float* l0, float* l1) {
+  float src = fmaf(scale, (float)dst + 0.5f, -0.5f); /* torch contracts this (bit-exact for s=2,3) */
+  if (src < 0.0f) src = 0.0f;
+  int a = (int)src;
+  if (a > n_in - 1) a = n_in - 1;
+  int b = a + 1 < n_in ? a + 1 : n_in - 1;
+  float lam = src - (float)a;
+  if (lam < 0.0f) lam = 0.0f;
+  if (lam > 1.0f) lam = 1.0f;
+  *i0 = a; *i1 = b; *l1 = lam; *l0 = 1.0f - lam;
+}
+
+static inline float orc_upsampled(const float* plane, int64_t sy, int64_t sx, int y0, int y1, float ly0, float ly1,
+                                  int x0, int x1, float lx0, float lx1) {
+  float v00 = plane[y0 * sy + x0 * sx], v01 = plane[y0 * sy + x1 * sx];
+  float v10 = plane[y1 * sy + x0 * sx], v11 = plane[y1 * sy + x1 * sx];
+  float top = fmaf(lx0, v00, lx1 * v01);
+  float bot = fmaf(lx0, v10, lx1 * v11);
+  return fmaf(ly0, top, ly1 * bot);
+}
+
+/* costs: element (b,d,y,x) at b*sb + d*sd + y*sy + x*sx  (channel 0 of [B,1,D,H,W], :52)
+ * interp != 0: out_h x out_w differs from in_h x in_w and the upsample runs (:54-60)
+ * inv_dist [B,1,Ho,Wo]; norm_costs [B,D,Ho,Wo] (may be NULL); argmax [B,Ho,Wo] (may be NULL) */
+void orc_softargmin(const float* costs, int64_t sb, int64_t sd, int64_t sy, int64_t sx, int B, int D, int Hin, int Win,
+                    int Hout, int Wout, int interp, float scale_h, float scale_w, const float* inv_dist_idx,
+                    float* inv_dist, float* norm_costs, int32_t* argmax) {
+  const int64_t HWo = (int64_t)Hout * Wout;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b)
+    for (int oy = 0; oy < Hout; ++oy) {
+      float* v = (float*)malloc(sizeof(float) * (size_t)D);
+      int y0 = oy, y1 = oy;
+      float ly0 = 1.0f, ly1 = 0.0f;
+      if (interp) orc_src_index(oy, scale_h, Hin, &y0, &y1, &ly0, &ly1);
+      for (int ox = 0; ox < Wout; ++ox) {
+        int x0 = ox, x1 = ox;
+        float lx0 = 1.0f, lx1 = 0.0f;
+        if (interp) orc_src_index(ox, scale_w, Win, &x0, &x1, &lx0, &lx1);
+        float mx = -INFINITY;
+        int am = 0;
+        for (int d = 0; d < D; ++d) {
+          const float* plane = costs + b * sb + d * sd;
+          v[d] = interp ? orc_upsampled(plane, sy, sx, y0, y1, ly0, ly1, x0, x1, lx0, lx1) : plane[oy * sy + ox * sx];
+          if (v[d] > mx) { mx = v[d]; am = d; }
+        }
+        /* :62 softmax over D: exp(x - max) / sum  (ATen SoftMaxKernel.cpp vec_softmax) */
+        float sum = 0.0f;
+        for (int d = 0; d < D; ++d) { v[d] = expf(v[d] - mx); sum += v[d]; }
+        /* :74-78 sum_d norm_costs * inv_dist_idx, sequential over d */
+        float acc = 0.0f;
+        for (int d = 0; d < D; ++d) {
+          float p = v[d] / sum;
+          if (norm_costs) norm_costs[((int64_t)b * D + d) * HWo + (int64_t)oy * Wout + ox] = p;
+          float term = p * inv_dist_idx[d];
+          acc = (d == 0) ? term : acc + term;
+        }
+        inv_dist[(int64_t)b * HWo + (int64_t)oy * Wout + ox] = acc;
+        if (argmax) argmax[(int64_t)b * HWo + (int64_t)oy * Wout + ox] = am;
+      }
+      free(v);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Grid precompute the fused kernel absorbs.           */
+/* A.1 Equirectangular.pixel_2_ray  dsta_mvs/mvs_utils/camera_models.py:680-720 */
+static inline void orc_cv_ray(const MvsgiRig* rig, int h, int w, float ray[3]) {
+  float px = (float)w + 0.5f, py = (float)h + 0.5f;
+  float lon = px / (float)rig->cv_width * rig->cv_lon_span_pixel + rig->cv_lon0;   /* :708 */
+  float lat = py / (float)rig->cv_height * rig->cv_lat_range + rig->cv_lat0;
+  float c = cosf(lat);
+  ray[0] = c * sinf(lon); /* :713-717 */
+  ray[1] = sinf(lat);
+  ray[2] = c * cosf(lon);
+}
+
+/* One camera model: point (x,y,z) in the camera frame -> normalised grid + valid. */
+static inline void orc_project(const MvsgiCamera* cam, float x, float y, float z, float* gx, float* gy, int* valid) {
+  const float* p = cam->p;
+  if (cam->model == MVSGI_CAM_EQUIRECT) {
+    /* Equirectangular.point_3d_2_pixel  camera_models.py:741-764 */
+    float lon0 = p[0], lon1 = p[1], lon_span = p[2], lat0 = p[3], lat_range = p[4];
+    float r = sqrtf(z * z + x * x);                 /* linalg.norm((z,x)) :745 */
+    float lat = atan2f(y, r);
+    float lon = atan2f(x, z);
+    float py = (lat - lat0) / lat_range;
+    /* radian.py:61-62 shift_according_2_range */
+    float two_pi = (float)(2.0 * M_PI);
+    lon = lon + two_pi * ((lon < lon0 ? 1.0f : 0.0f) - (lon > lon1 ? 1.0f : 0.0f));
+    float px = (lon - lon0) / lon_span;
+    *valid = (px >= 0.0f) && (px <= 1.0f) && (py >= 0.0f) && (py <= 1.0f); /* :759 */
+    *gx = px * 2.0f - 1.0f;
+    *gy = py * 2.0f - 1.0f;
+  } else if (cam->model == MVSGI_CAM_DOUBLE_SPHERE) {
+    /* DoubleSphere.point_3d_2_pixel  camera_models.py:492-529 */
+    float xi = p[0], alpha = p[1], oma = p[2], fx = p[3], fy = p[4], cx = p[5], cy = p[6], neg_w2 = p[7],
+          half_fov = p[8];
+    float x2 = x * x, y2 = y * y, z2 = z * z;
+    float d1 = sqrtf(x2 + y2 + z2);
+    float xd = xi * d1 + z;
+    float d2 = sqrtf(x2 + y2 + xd * xd);
+    float t = alpha * d2 + oma * xd;
+    float px = fx / t * x + cx;
+    float py = fy / t * y + cy;
+    *gx = px / (float)cam->width * 2.0f - 1.0f;  /* :515-516 */
+    *gy = py / (float)cam->height * 2.0f - 1.0f;
+    float a = atan2f(sqrtf(x2 + y2), z);         /* :525 x2y2z_2_z_angle */
+    *valid = (z > neg_w2 * d1) && (a <= half_fov);
+  } else {
+    /* LinearSphere.point_3d_2_pixel  camera_models.py:1506-1548 */
+    float fov = p[0];
+    float W = (float)cam->width, H = (float)cam->height;
+    float R = sqrtf(x * x + y * y + z * z);      /* (x2+y2+z2)**0.5 */
+    float ph = acosf(z / R);
+    float th = atan2f(y, x);
+    float r = ph * W / fov;
+    float u = r * cosf(th) + W / 2.0f;
+    float v = r * sinf(th) + H / 2.0f;
+    *valid = (u >= 0.0f) && (u < W) && (v >= 0.0f) && (v < H);
+    *gx = u / W * 2.0f - 1.0f;
+    *gy = v / H * 2.0f - 1.0f;
+  }
+}
+
+/* create_grids_from_rays  multi_view_camera_model_dataset.py:530-557 (+ :474-518):
+ * grids [CAM,D,Ho,Wo,2], grid_masks [CAM,D,Ho,Wo] */
+void orc_make_grids(const MvsgiRig* rig, float* grids, uint8_t* grid_masks) {
+  const int Ho = rig->cv_height, Wo = rig->cv_width, D = rig->num_cands;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int cam = 0; cam < rig->num_cams; ++cam)
+    for (int d = 0; d < D; ++d)
+      for (int h = 0; h < Ho; ++h)
+        for (int w = 0; w < Wo; ++w) {
+          const MvsgiCamera* c = &rig->cams[cam];
+          float ray[3];
+          orc_cv_ray(rig, h, w, ray);
+          /* torch_cuda_sweep.py:206-209  rays * candidates */
+          float X = ray[0] * rig->dist[d], Y = ray[1] * rig->dist[d], Z = ray[2] * rig->dist[d];
+          /* torch_cuda_sweep.py:398-403  R @ p + t  (inverse pose, ftensor.py:470-476) */
+          float x = (c->rot[0] * X + c->rot[1] * Y) + c->rot[2] * Z + c->trans[0];
+          float y = (c->rot[3] * X + c->rot[4] * Y) + c->rot[5] * Z + c->trans[1];
+          float z = (c->rot[6] * X + c->rot[7] * Y) + c->rot[8] * Z + c->trans[2];
+          float gx, gy;
+          int valid;
+          orc_project(c, x, y, z, &gx, &gy, &valid);
+          int64_t o = (((int64_t)cam * D + d) * Ho + h) * Wo + w;
+          grids[o * 2 + 0] = gx;
+          grids[o * 2 + 1] = gy;
+          grid_masks[o] = (uint8_t)valid;
+        }
+}
+
+/* float64 restatement of the same geometry: the yardstick for "how far may the
+ * kernel's fp32 grid be from the truth" (SURVEY.md §7 H2 / §8c criterion 3b). */
+void orc_make_grids_f64(const MvsgiRig* rig, double* grids, uint8_t* grid_masks) {
+  const int Ho = rig->cv_height, Wo = rig->cv_width, D = rig->num_cands;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int cam = 0; cam < rig->num_cams; ++cam)
+    for (int d = 0; d < D; ++d)
+      for (int h = 0; h < Ho; ++h)
+        for (int w = 0; w < Wo; ++w) {
+          const MvsgiCamera* c = &rig->cams[cam];
+          const float* p = c->p;
+          double lon = (w + 0.5) / Wo * (double)rig->cv_lon_span_pixel + (double)rig->cv_lon0;
+          double lat = (h + 0.5) / Ho * (double)rig->cv_lat_range + (double)rig->cv_lat0;
+          double cl = cos(lat), dist = rig->dist[d];
+          double X = cl * sin(lon) * dist, Y = sin(lat) * dist, Z = cl * cos(lon) * dist;
+          double x = c->rot[0] * X + c->rot[1] * Y + c->rot[2] * Z + c->trans[0];
+          double y = c->rot[3] * X + c->rot[4] * Y + c->rot[5] * Z + c->trans[1];
+          double z = c->rot[6] * X + c->rot[7] * Y + c->rot[8] * Z + c->trans[2];
+          double gx, gy;
+          int valid;
+          if (c->model == MVSGI_CAM_EQUIRECT) {
+            double la = atan2(y, sqrt(z * z + x * x)), lo = atan2(x, z);
+            double py = (la - p[3]) / p[4];
+            lo += 2.0 * M_PI * ((lo < p[0] ? 1.0 : 0.0) - (lo > p[1] ? 1.0 : 0.0));
+            double px = (lo - p[0]) / p[2];
+            valid = px >= 0 && px <= 1 && py >= 0 && py <= 1;
+            gx = px * 2 - 1; gy = py * 2 - 1;
+          } else if (c->model == MVSGI_CAM_DOUBLE_SPHERE) {
+            double d1 = sqrt(x * x + y * y + z * z), xd = p[0] * d1 + z;
+            double d2 = sqrt(x * x + y * y + xd * xd);
+            double t = p[1] * d2 + p[2] * xd;
+            gx = (p[3] / t * x + p[5]) / c->width * 2 - 1;
+            gy = (p[4] / t * y + p[6]) / c->height * 2 - 1;
+            valid = (z > p[7] * d1) && (atan2(sqrt(x * x + y * y), z) <= p[8]);
+          } else {
+            double R = sqrt(x * x + y * y + z * z), ph = acos(z / R), th = atan2(y, x);
+            double r = ph * c->width / p[0];
+            double u = r * cos(th) + c->width / 2.0, v = r * sin(th) + c->height / 2.0;
+            valid = u >= 0 && u < c->width && v >= 0 && v < c->height;
+            gx = u / c->width * 2 - 1; gy = v / c->height * 2 - 1;
+          }
+          int64_t o = (((int64_t)cam * D + d) * Ho + h) * Wo + w;
+          grids[o * 2 + 0] = gx;
+          grids[o * 2 + 1] = gy;
+          grid_masks[o] = (uint8_t)valid;
+        }
+}
+
+int orc_num_threads(void) {
+#if defined(_OPENMP)
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
