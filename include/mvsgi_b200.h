@@ -59,6 +59,8 @@ enum {
 enum { MVSGI_MASK_F32 = 0, MVSGI_MASK_U8 = 1 };
 /* flags for MvsgiSweepArgs.flags */
 #define MVSGI_FLAG_FEATS_BF16 1u /* stage features as bf16 (fp32 accumulate); stated-tolerance mode */
+#define MVSGI_FLAG_STAGE_ONLY 2u /* only fill the workspace (channels-last feats, packed masks)          */
+#define MVSGI_FLAG_SWEEP_ONLY 4u /* workspace already holds what STAGE_ONLY produced for these args      */
 
 /* ---- calibration ------------------------------------------------------- */
 /* One camera the sweep projects into.  rot/trans are the INVERSE pose

@@ -19,6 +19,8 @@ GRID_SUPPLIED, GRID_PROJECT = 0, 1
 AGG_STD, AGG_CONCAT = 0, 1
 MASK_F32, MASK_U8 = 0, 1
 FLAG_FEATS_BF16 = 1
+FLAG_STAGE_ONLY = 2
+FLAG_SWEEP_ONLY = 4
 
 LIB_NAME = "libmvsgi_b200.so"
 _PKG_DIR = Path(__file__).resolve().parent

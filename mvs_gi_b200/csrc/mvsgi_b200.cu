@@ -1,0 +1,350 @@
+// mvsgi_b200.cu — C-ABI entry points of libmvsgi_b200.so (see include/mvsgi_b200.h).
+// Host side: argument validation, workspace carving, launch configuration.  No allocation, no sync.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "softargmin.cuh"
+#include "sweep.cuh"
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+struct SweepPlan {
+  bool stage_feats;       // feats are not channels-last: transpose into the workspace first
+  bool pack_masks;        // std builder: masks -> bit images
+  bool per_frame_masks;
+  bool per_frame_grids;
+  int n_mask_images;      // B*CAM or CAM
+  int mask_pitch;
+  int64_t feats_bytes, mask_bytes, flag_bytes, total_bytes;
+  int tile_h, dch, num_chunks, tiles_x, tiles_y;
+  size_t smem_bytes;
+  int cout;
+};
+
+int mask_pitch_words(int mask_w) { return (mask_w + 2 + 31) / 32 + 1; }
+
+bool is_channels_last(const MvsgiSweepArgs* a) {
+  const int64_t* s = a->feats_stride;  // B, CAM, C, H, W
+  if (s[2] != 1) return false;
+  if ((reinterpret_cast<uintptr_t>(a->feats) & 15) != 0) return false;
+  for (int i : {0, 1, 3, 4})
+    if (s[i] % 4 != 0) return false;
+  // in-image offsets are kept in int32
+  if (s[3] * a->feat_h >= (1ll << 31) || s[4] * a->feat_w >= (1ll << 31)) return false;
+  return true;
+}
+
+int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
+  if (a == nullptr) return MVSGI_E_NULL;
+  if (a->struct_size != sizeof(MvsgiSweepArgs)) return MVSGI_E_VERSION;
+  if (a->aggregate != MVSGI_AGG_STD && a->aggregate != MVSGI_AGG_CONCAT) return MVSGI_E_UNSUPPORTED;
+  if (a->grid_mode != MVSGI_GRID_SUPPLIED && a->grid_mode != MVSGI_GRID_PROJECT) return MVSGI_E_UNSUPPORTED;
+  if (a->flags & ~(MVSGI_FLAG_FEATS_BF16 | MVSGI_FLAG_STAGE_ONLY | MVSGI_FLAG_SWEEP_ONLY)) return MVSGI_E_UNSUPPORTED;
+  if ((a->flags & MVSGI_FLAG_STAGE_ONLY) && (a->flags & MVSGI_FLAG_SWEEP_ONLY)) return MVSGI_E_UNSUPPORTED;
+  if (a->flags & MVSGI_FLAG_FEATS_BF16) return MVSGI_E_UNSUPPORTED;  // reserved; fp32 staging only for now
+  if (a->batch <= 0 || a->feat_chs <= 0 || a->out_h <= 0 || a->out_w <= 0) return MVSGI_E_SHAPE;
+  if (a->num_cams < 1 || a->num_cams > MVSGI_MAX_CAMS) return MVSGI_E_SHAPE;
+  if (a->num_cands < 1) return MVSGI_E_SHAPE;
+  if (a->feat_h < 2 || a->feat_w < 2) return MVSGI_E_SHAPE;
+  if (a->feat_chs % 4 != 0) return MVSGI_E_SHAPE;  // 16-byte taps
+  if (a->feats == nullptr || a->vol == nullptr) return MVSGI_E_NULL;
+  const bool std_agg = a->aggregate == MVSGI_AGG_STD;
+  if (std_agg) {
+    if (a->masks == nullptr) return MVSGI_E_NULL;
+    if (a->mask_h < 1 || a->mask_w < 1) return MVSGI_E_SHAPE;
+    if (a->masks_dtype != MVSGI_MASK_F32 && a->masks_dtype != MVSGI_MASK_U8) return MVSGI_E_UNSUPPORTED;
+    if ((int64_t)(a->mask_h + 2) * mask_pitch_words(a->mask_w) * 32 >= (1ll << 28)) return MVSGI_E_SHAPE;
+  }
+  if (a->grid_mode == MVSGI_GRID_PROJECT) {
+    if (a->rig == nullptr) return MVSGI_E_NULL;
+    if (a->rig->num_cams != a->num_cams || a->rig->num_cands != a->num_cands) return MVSGI_E_SHAPE;
+    if (a->rig->cv_height != a->out_h || a->rig->cv_width != a->out_w) return MVSGI_E_SHAPE;
+    if (a->num_cands > MVSGI_MAX_CANDS) return MVSGI_E_SHAPE;
+    for (int i = 0; i < a->num_cams; ++i)
+      if (a->rig->cams[i].model < 0 || a->rig->cams[i].model > MVSGI_CAM_LINEAR_SPHERE) return MVSGI_E_UNSUPPORTED;
+  } else {
+    if (a->grids == nullptr) return MVSGI_E_NULL;
+    if (std_agg && a->grid_masks == nullptr) return MVSGI_E_NULL;
+    if ((reinterpret_cast<uintptr_t>(a->grids) & 7) != 0) return MVSGI_E_STRIDE;
+    for (int i = 0; i < 5; ++i)
+      if (a->grids_stride[i] % 2 != 0) return MVSGI_E_STRIDE;  // float2 loads
+  }
+
+  p->cout = std_agg ? a->feat_chs : a->feat_chs * a->num_cams;
+  p->stage_feats = !is_channels_last(a);
+  p->pack_masks = std_agg;
+  p->per_frame_masks = std_agg && a->batch > 1 && a->masks_stride[0] != 0;
+  p->per_frame_grids = a->grid_mode == MVSGI_GRID_SUPPLIED && a->batch > 1 &&
+                       (a->grids_stride[0] != 0 || (std_agg && a->grid_masks_stride[0] != 0));
+  p->n_mask_images = std_agg ? (p->per_frame_masks ? a->batch : 1) * a->num_cams : 0;
+  p->mask_pitch = std_agg ? mask_pitch_words(a->mask_w) : 0;
+  p->feats_bytes =
+      p->stage_feats ? align_up((int64_t)a->batch * a->num_cams * a->feat_h * a->feat_w * a->feat_chs * 4, 256) : 0;
+  p->mask_bytes = align_up((int64_t)p->n_mask_images * (a->mask_h + 2) * p->mask_pitch * 4, 256);
+  p->flag_bytes = 256;
+  p->total_bytes = p->feats_bytes + p->mask_bytes + p->flag_bytes;
+
+  // tile / candidate-chunk shape: 2 x 32 pixels, up to 16 candidates per chunk, table capped at ~64 KB so that two
+  // CTAs per SM still leave >= 96 KB of the 228 KB unified array as L1 for the gathers.
+  p->tile_h = env_int("MVSGI_TILE_H", 2);
+  if (p->tile_h != 1 && p->tile_h != 2 && p->tile_h != 4) p->tile_h = 2;
+  const int tp = p->tile_h * mvsgi::kTileW;
+  const int bytes_per_ent = 20 + (p->per_frame_masks ? 4 : 0);
+  int dch = env_int("MVSGI_DCH", 16);
+  if (dch < 1) dch = 1;
+  if (dch > a->num_cands) dch = a->num_cands;
+  const int budget = env_int("MVSGI_TABLE_BYTES", 64 * 1024);
+  while (dch > 1 && (int64_t)dch * a->num_cams * tp * bytes_per_ent > budget) dch = (dch + 1) / 2;
+  p->dch = dch;
+  p->num_chunks = (a->num_cands + dch - 1) / dch;
+  p->tiles_x = (a->out_w + mvsgi::kTileW - 1) / mvsgi::kTileW;
+  p->tiles_y = (a->out_h + p->tile_h - 1) / p->tile_h;
+  p->smem_bytes = (size_t)dch * a->num_cams * tp * bytes_per_ent + (size_t)dch * tp + 16;
+  return MVSGI_OK;
+}
+
+template <int CAM, int AGG>
+cudaError_t launch_sweep(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, int threads, size_t smem,
+                         cudaStream_t st) {
+  auto kern = mvsgi::sweep_kernel<CAM, AGG>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, threads, smem, st>>>(kp, rig);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+template <int AGG>
+cudaError_t dispatch_cams(int cams, const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, int threads, size_t smem,
+                          cudaStream_t st) {
+  switch (cams) {
+    case 1: return launch_sweep<1, AGG>(kp, rig, grid, threads, smem, st);
+    case 2: return launch_sweep<2, AGG>(kp, rig, grid, threads, smem, st);
+    case 3: return launch_sweep<3, AGG>(kp, rig, grid, threads, smem, st);
+    default: return launch_sweep<4, AGG>(kp, rig, grid, threads, smem, st);
+  }
+}
+
+cudaError_t launch_pack(const void* masks, int dtype, int n0, int64_t s0, int n1, int64_t s1, int64_t sh, int64_t sw,
+                        int Hm, int Wm, uint32_t* bits, int* flags, cudaStream_t st) {
+  const int pitch = mask_pitch_words(Wm);
+  dim3 grid((pitch + 7) / 8, Hm + 2, n0 * n1);
+  if (dtype == MVSGI_MASK_F32)
+    mvsgi::pack_masks_kernel<float><<<grid, 256, 0, st>>>((const float*)masks, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits,
+                                                          flags);
+  else
+    mvsgi::pack_masks_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)masks, n1, s0, s1, sh, sw, Hm, Wm, pitch,
+                                                            bits, flags);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int mvsgi_abi_version(void) { return MVSGI_ABI_VERSION; }
+
+int64_t mvsgi_launch_counter(void) { return g_launches.load(); }
+
+const char* mvsgi_strerror(int code) {
+  switch (code) {
+    case MVSGI_OK: return "ok";
+    case MVSGI_E_NULL: return "required pointer is NULL";
+    case MVSGI_E_SHAPE: return "bad shape (size <= 0, over a limit, feat_chs not a multiple of 4, or rig/shape mismatch)";
+    case MVSGI_E_STRIDE: return "unsupported stride or alignment";
+    case MVSGI_E_UNSUPPORTED: return "unsupported enum value or flag";
+    case MVSGI_E_WORKSPACE: return "workspace too small or not 256-byte aligned";
+    case MVSGI_E_VERSION: return "struct_size does not match this library (ABI mismatch)";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown mvsgi error";
+  }
+}
+
+int32_t mvsgi_mask_pitch_words(int32_t mask_w) { return mask_pitch_words(mask_w); }
+
+int64_t mvsgi_sweep_workspace_bytes(const MvsgiSweepArgs* a) {
+  SweepPlan p;
+  const int rc = validate_and_plan(a, &p);
+  return rc != MVSGI_OK ? (int64_t)rc : p.total_bytes;
+}
+
+int mvsgi_sweep_launch_count(const MvsgiSweepArgs* a) {
+  SweepPlan p;
+  const int rc = validate_and_plan(a, &p);
+  if (rc != MVSGI_OK) return rc;
+  const int stage = (p.stage_feats ? 1 : 0) + (p.pack_masks ? 1 : 0);
+  if (a->flags & MVSGI_FLAG_STAGE_ONLY) return stage;
+  if (a->flags & MVSGI_FLAG_SWEEP_ONLY) return 1;
+  return 1 + stage;
+}
+
+int mvsgi_pack_masks(const void* masks, int32_t dtype, int32_t n_outer, int64_t stride_outer, int32_t n_inner,
+                     int64_t stride_inner, int64_t stride_h, int64_t stride_w, int32_t mask_h, int32_t mask_w,
+                     uint32_t* bits_out, int32_t* flags_out, void* stream) {
+  if (masks == nullptr || bits_out == nullptr) return MVSGI_E_NULL;
+  if (n_outer < 1 || n_inner < 1 || mask_h < 1 || mask_w < 1) return MVSGI_E_SHAPE;
+  if (dtype != MVSGI_MASK_F32 && dtype != MVSGI_MASK_U8) return MVSGI_E_UNSUPPORTED;
+  return (int)launch_pack(masks, dtype, n_outer, stride_outer, n_inner, stride_inner, stride_h, stride_w, mask_h,
+                          mask_w, bits_out, flags_out, (cudaStream_t)stream);
+}
+
+int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
+  SweepPlan p;
+  int rc = validate_and_plan(a, &p);
+  if (rc != MVSGI_OK) return rc;
+  if (p.total_bytes > 0) {
+    if (a->workspace == nullptr) return MVSGI_E_NULL;
+    if (a->workspace_bytes < p.total_bytes || (reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0)
+      return MVSGI_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)a->workspace;
+  float* ws_feats = (float*)ws;
+  uint32_t* ws_bits = (uint32_t*)(ws + p.feats_bytes);
+  int* ws_flags = (int*)(ws + p.feats_bytes + p.mask_bytes);
+  const bool std_agg = a->aggregate == MVSGI_AGG_STD;
+  const bool do_stage = !(a->flags & MVSGI_FLAG_SWEEP_ONLY);
+  const bool do_sweep = !(a->flags & MVSGI_FLAG_STAGE_ONLY);
+
+  mvsgi::SweepKP kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.B = a->batch; kp.C = a->feat_chs; kp.D = a->num_cands; kp.Cout = p.cout;
+  kp.Ho = a->out_h; kp.Wo = a->out_w; kp.Hf = a->feat_h; kp.Wf = a->feat_w; kp.Hm = a->mask_h; kp.Wm = a->mask_w;
+  kp.tileH = p.tile_h; kp.dch = p.dch; kp.numChunks = p.num_chunks; kp.tilesX = p.tiles_x;
+  kp.numTiles = p.tiles_x * p.tiles_y;
+  kp.totalItems = (long long)kp.numTiles * p.num_chunks * a->batch;
+
+  // 1. features -> channels-last
+  if (p.stage_feats) {
+    const int N = a->batch * a->num_cams;
+    dim3 grid((a->feat_w + 31) / 32, a->feat_h, N);
+    const size_t smem = (size_t)a->feat_chs * 33 * sizeof(float);
+    if (smem > 48 * 1024) return MVSGI_E_SHAPE;
+    if (do_stage) {
+      mvsgi::nhwc_stage_kernel<<<grid, 256, smem, st>>>(a->feats, a->feats_stride[0], a->num_cams, a->feats_stride[1],
+                                                        a->feats_stride[2], a->feats_stride[3], a->feats_stride[4],
+                                                        a->feat_chs, a->feat_h, a->feat_w, ws_feats);
+      g_launches++;
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return (int)e;
+    }
+    kp.feat = ws_feats;
+    kp.fsX = a->feat_chs;
+    kp.fsY = a->feat_w * a->feat_chs;
+    kp.fsCam = (long long)a->feat_h * kp.fsY;
+    kp.fsB = kp.fsCam * a->num_cams;
+  } else {
+    kp.feat = a->feats;
+    kp.fsB = a->feats_stride[0]; kp.fsCam = a->feats_stride[1];
+    kp.fsY = (int)a->feats_stride[3]; kp.fsX = (int)a->feats_stride[4];
+  }
+
+  // 2. masks -> bits
+  if (p.pack_masks) {
+    if (do_stage) {
+      cudaError_t e = launch_pack(a->masks, a->masks_dtype, p.per_frame_masks ? a->batch : 1, a->masks_stride[0],
+                                  a->num_cams, a->masks_stride[1], a->masks_stride[2], a->masks_stride[3], a->mask_h,
+                                  a->mask_w, ws_bits, ws_flags, st);
+      if (e != cudaSuccess) return (int)e;
+    }
+    kp.mbits = ws_bits;
+    kp.mPitch = p.mask_pitch;
+    kp.mbCam = (long long)(a->mask_h + 2) * p.mask_pitch;
+    kp.mbB = kp.mbCam * a->num_cams;
+    kp.perFrameMasks = p.per_frame_masks ? 1 : 0;
+  }
+
+  // 3. the sweep
+  if (!do_sweep) return MVSGI_OK;
+  kp.gridMode = a->grid_mode;
+  kp.perFrameGrids = p.per_frame_grids ? 1 : 0;
+  if (a->grid_mode == MVSGI_GRID_SUPPLIED) {
+    kp.grids = a->grids;
+    kp.gsB = a->grids_stride[0]; kp.gsCam = a->grids_stride[1]; kp.gsD = a->grids_stride[2];
+    kp.gsY = a->grids_stride[3]; kp.gsX = a->grids_stride[4];
+    if (std_agg) {
+      kp.gmask = a->grid_masks;
+      kp.gmB = a->grid_masks_stride[0]; kp.gmCam = a->grid_masks_stride[1]; kp.gmD = a->grid_masks_stride[2];
+      kp.gmY = a->grid_masks_stride[3]; kp.gmX = a->grid_masks_stride[4];
+    }
+  }
+  kp.vol = a->vol;
+  kp.validOut = std_agg ? a->valid_out : nullptr;
+
+  MvsgiRig rig;
+  if (a->grid_mode == MVSGI_GRID_PROJECT) rig = *a->rig;
+  else memset(&rig, 0, sizeof(rig));
+
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int threads = p.tile_h * mvsgi::kTileW * mvsgi::kLanesPerPixel;
+  int ctas_per_sm = env_int("MVSGI_CTAS_PER_SM", 0);
+  if (ctas_per_sm <= 0) {
+    ctas_per_sm = (int)((200 * 1024) / (p.smem_bytes + 1024));
+    const int by_threads = 1536 / threads;  // leave the rest of the 228 KB array to L1
+    if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
+    if (ctas_per_sm > 2) ctas_per_sm = 2;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  long long grid = (long long)sms * ctas_per_sm;
+  if (grid > kp.totalItems) grid = kp.totalItems;
+  cudaError_t e = std_agg ? dispatch_cams<MVSGI_AGG_STD>(a->num_cams, kp, rig, (int)grid, threads, p.smem_bytes, st)
+                          : dispatch_cams<MVSGI_AGG_CONCAT>(a->num_cams, kp, rig, (int)grid, threads, p.smem_bytes, st);
+  return (int)e;
+}
+
+int mvsgi_project_only_f32(const MvsgiProjectArgs* a, void* stream) {
+  if (a == nullptr || a->rig == nullptr || a->grids == nullptr || a->grid_masks == nullptr) return MVSGI_E_NULL;
+  if (a->struct_size != sizeof(MvsgiProjectArgs)) return MVSGI_E_VERSION;
+  const MvsgiRig& r = *a->rig;
+  if (r.num_cams < 1 || r.num_cams > MVSGI_MAX_CAMS || r.num_cands < 1 || r.num_cands > MVSGI_MAX_CANDS ||
+      r.cv_width < 1 || r.cv_height < 1)
+    return MVSGI_E_SHAPE;
+  const int n = r.cv_width * r.cv_height;
+  mvsgi::project_only_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r, a->grids, a->grid_masks);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int mvsgi_softargmin_f32(const MvsgiSoftArgminArgs* a, void* stream) {
+  if (a == nullptr) return MVSGI_E_NULL;
+  if (a->struct_size != sizeof(MvsgiSoftArgminArgs)) return MVSGI_E_VERSION;
+  if (a->costs == nullptr || a->inv_dist_idx == nullptr || a->inv_dist == nullptr) return MVSGI_E_NULL;
+  if (a->batch < 1 || a->num_cands < 1 || a->num_cands > MVSGI_MAX_CANDS || a->in_h < 1 || a->in_w < 1 ||
+      a->out_h < 1 || a->out_w < 1 || a->batch > 65535 || a->out_h > 65535)
+    return MVSGI_E_SHAPE;
+  mvsgi::SoftKP kp;
+  kp.B = a->batch; kp.D = a->num_cands; kp.Hin = a->in_h; kp.Win = a->in_w; kp.Hout = a->out_h; kp.Wout = a->out_w;
+  kp.interp = (a->out_h != a->in_h || a->out_w != a->in_w) ? 1 : 0;
+  kp.scaleH = a->src_scale_h; kp.scaleW = a->src_scale_w;
+  kp.costs = a->costs;
+  kp.sB = a->costs_stride[0]; kp.sD = a->costs_stride[1]; kp.sY = a->costs_stride[2]; kp.sX = a->costs_stride[3];
+  kp.idx = a->inv_dist_idx; kp.invDist = a->inv_dist; kp.normCosts = a->norm_costs; kp.argmax = a->argmax;
+  int split = a->num_cands <= 16 ? 1 : (a->num_cands <= 32 ? 2 : 4);
+  const int forced = env_int("MVSGI_SOFTARGMIN_DSPLIT", 0);
+  if (forced == 1 || forced == 2 || forced == 4) {
+    if ((a->num_cands + forced - 1) / forced <= 16) split = forced;
+  }
+  const int ppb = 4 * (32 / split);  // output pixels per 128-thread block
+  dim3 grid((a->out_w + ppb - 1) / ppb, a->out_h, a->batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (split == 1) mvsgi::softargmin_kernel<1><<<grid, 128, 0, st>>>(kp);
+  else if (split == 2) mvsgi::softargmin_kernel<2><<<grid, 128, 0, st>>>(kp);
+  else mvsgi::softargmin_kernel<4><<<grid, 128, 0, st>>>(kp);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

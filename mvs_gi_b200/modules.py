@@ -1,0 +1,223 @@
+"""Drop-in nn.Modules for the reference's sweep / cv_builder / distance-regression components.
+
+Same constructor arguments, attributes, method signatures, state_dict keys and
+error behaviour as the reference classes they replace, so a Lightning model or
+api/inference_pytorch.py can swap them in:
+
+  SphericalSweepStdMasked   dsta_mvs/model/cost_volume_builder/spherical_sweep_avg.py:9-167
+  SphericalSweep            dsta_mvs/model/cost_volume_builder/spherical_sweep.py:9-102
+  DistanceRegressorWithFixedCandidates
+                            dsta_mvs/model/distance_regressor/distance_regressor.py:7-80
+
+The sweep itself runs in the fused sm_100a kernel; `post_vol` (Conv3d + BatchNorm3d
++ LeakyReLU, dsta_mvs/model/common/common_modules.py:82-115) stays on cuDNN as in
+the reference and keeps its parameter names (`post_vol.conv_layer.weight`,
+`post_vol.norm_layer.*`).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor, nn
+
+from . import abi, ops
+from .calibration import Rig
+
+
+class _NoOp(nn.Module):
+    def forward(self, x):
+        return x
+
+
+# dsta_mvs/model/common/__init__.py:7-23
+RELU_TYPE = {"original": nn.ReLU, "leaky": nn.LeakyReLU, "none": _NoOp}
+NORM3D_TYPE = {"batch": nn.BatchNorm3d, "instance": nn.InstanceNorm3d, "none": _NoOp}
+
+
+class _ConvBlk3d(nn.Module):
+    """Conv3d -> norm -> activation with the reference's sub-module names (common_modules.py:82-115)."""
+
+    def __init__(self, in_chs: int, out_chs: int, kernel_size: int, norm_layer: nn.Module, activation: nn.Module):
+        super().__init__()
+        self.conv_layer = nn.Conv3d(in_chs, out_chs, kernel_size, padding=kernel_size // 2, bias=False, stride=1)
+        self.norm_layer = norm_layer
+        self.activation = activation
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.activation(self.norm_layer(self.conv_layer(x)))
+
+
+def _reject_autograd(feats: Tensor) -> None:
+    if torch.is_grad_enabled() and feats.requires_grad:
+        raise NotImplementedError(
+            "mvs_gi_b200: the fused sweep is forward-only (SURVEY.md §8 row f1 'backward' is not built yet); "
+            "wrap inference in torch.no_grad() or keep the reference module for training")
+
+
+class _SweepBase(nn.Module):
+    _aggregate = abi.AGG_STD
+
+    def __init__(self, num_cams: int, feat_chs: int, post_k_sz: int, norm_type: str = "batch",
+                 relu_type: str = "leaky"):
+        super().__init__()
+        self.num_cams = num_cams
+        self.feat_chs = feat_chs
+        self.norm_type = NORM3D_TYPE[norm_type]
+        self.relu_type = RELU_TYPE[relu_type]
+        self.grid_sample_mode = "bilinear"
+        self.post_vol = _ConvBlk3d(self.feat_chs, self.feat_chs, post_k_sz, norm_layer=self.norm_type(self.feat_chs),
+                                   activation=self.relu_type())
+        # Fused in-kernel projection (north_star (b)): when a rig is attached, `grids`/`grid_masks` passed to
+        # forward() are ignored and never read from HBM.
+        self._rig: Optional[Rig] = None
+        self._rig_blob: Optional[Tensor] = None
+        self._static_masks: Optional[Tensor] = None
+
+    # ---- B200-specific configuration (not part of the reference interface) ----
+    def attach_rig(self, rig: Optional[Rig]) -> "_SweepBase":
+        """Evaluate the sampling grid in-kernel from this calibration instead of reading `grids`."""
+        self._rig = rig
+        self._rig_blob = ops.rig_to_blob(rig.to_struct()) if rig is not None else None
+        return self
+
+    def set_static_masks(self, masks: Optional[Tensor]) -> "_SweepBase":
+        """Inference: masks are the same for every frame ([1|B, CAM, 1, Hm, Wm]); only frame 0 is kept and shared."""
+        self._static_masks = None if masks is None else masks[:1].contiguous()
+        return self
+
+    @classmethod
+    def from_reference(cls, module: nn.Module) -> "_SweepBase":
+        """Build from a reference cv_builder instance, carrying over post_vol parameters and buffers."""
+        k = module.post_vol.conv_layer.kernel_size[0]
+        norm = {v: k_ for k_, v in NORM3D_TYPE.items()}.get(type(module.post_vol.norm_layer), "none")
+        relu = {v: k_ for k_, v in RELU_TYPE.items()}.get(type(module.post_vol.activation), "none")
+        new = cls(module.num_cams, module.feat_chs, k, norm, relu)
+        new.post_vol.load_state_dict(module.post_vol.state_dict())
+        new.train(module.training)
+        return new.to(next(module.parameters()).device)
+
+    def _run(self, feats: Tensor, grids, grid_masks, masks, want_valid: bool = False):
+        _reject_autograd(feats)
+        if feats.shape[1] != self.num_cams:
+            raise RuntimeError(f"expected {self.num_cams} cameras, feats has {feats.shape[1]}")
+        if self._rig_blob is not None:
+            rig = self._rig
+            D, Ho, Wo = rig.num_cands, rig.cv_camera.H, rig.cv_camera.W
+            grids = grid_masks = None
+        else:
+            D, Ho, Wo = grids.shape[2:5]
+        if self._aggregate == abi.AGG_STD and self._static_masks is not None:
+            masks = self._static_masks
+        return ops.sweep_op(feats, grids, grid_masks, masks if self._aggregate == abi.AGG_STD else None,
+                            self._rig_blob, self._aggregate, int(Ho), int(Wo), int(D), want_valid)
+
+
+class SphericalSweepStdMasked(_SweepBase):
+    """Masked mean/variance sweep (reference spherical_sweep_avg.py:9)."""
+
+    _aggregate = abi.AGG_STD
+
+    def sweep(self, feats: Tensor, grids: Tensor, grid_masks: Tensor, masks: Tensor) -> Tensor:
+        """feats [B,CAM,C,Hi,Wi], grids [B,CAM,X,Ho,Wo,2], grid_masks [B,CAM,X,Ho,Wo,1], masks [B,CAM,1,Hm,Wm]
+        -> vol [B,C,X,Ho,Wo]   (reference :38-136)."""
+        return self._run(feats, grids, grid_masks, masks)[0]
+
+    def sweep_with_valid(self, feats, grids, grid_masks, masks):
+        """Also returns the validity mask (n>1 cameras, reference :106-108) the reference never exposes."""
+        vol, valid = self._run(feats, grids, grid_masks, masks, want_valid=True)
+        return vol, valid.bool()
+
+    def forward(self, feats: Tensor, grids: Tensor, grid_masks: Tensor, masks: Tensor) -> Tensor:
+        return self.post_vol(self.sweep(feats, grids, grid_masks, masks))  # reference :162-167
+
+
+class SphericalSweep(_SweepBase):
+    """Concat sweep (reference spherical_sweep.py:9); feat_chs = CAM * C of the extractor."""
+
+    _aggregate = abi.AGG_CONCAT
+
+    def sweep(self, feats: Tensor, grids: Tensor, masks: Optional[Tensor] = None) -> Tensor:
+        """-> vol [B, CAM*C, X, Ho, Wo], channel = cam*C + c (reference :38-68); masks unused."""
+        return self._run(feats, grids, None, None)[0]
+
+    def forward(self, feats: Tensor, grids: Tensor, grid_masks: Tensor, masks: Tensor) -> Tensor:
+        # grid_masks is not used; it is here for compatibility (reference :81).
+        return self.post_vol(self.sweep(feats, grids, masks))
+
+
+class DistanceRegressorWithFixedCandidates(nn.Module):
+    """Soft-argmin over fixed distance candidates (reference distance_regressor.py:7-80)."""
+
+    def __init__(self, bf: float = 96, dist_cands: Sequence[float] = (0.5, 1, 1.5, 2, 5, 10, 20, 30, 50, 100),
+                 interp_scale_factor: float = 0, pre_interp: bool = False):
+        super().__init__()
+        inv_dist_idx = bf / torch.tensor(list(dist_cands), dtype=torch.float32)
+        self.register_buffer("inv_dist_idx", inv_dist_idx.view(1, -1, 1, 1), persistent=True)
+        self.inv_dist_idx_min = float(torch.min(self.inv_dist_idx))
+        self.inv_dist_idx_max = float(torch.max(self.inv_dist_idx))
+        self.bf = bf
+        self.interp_scale_factor = interp_scale_factor if interp_scale_factor > 0 else 0
+        self.pre_interp = pre_interp
+        # inference callers (torch_only.py:34, api/) drop norm_costs; set False to skip writing 6.5 MB/frame
+        self.return_norm_costs = True
+
+    @classmethod
+    def from_reference(cls, module: nn.Module) -> "DistanceRegressorWithFixedCandidates":
+        cands = (module.bf / module.inv_dist_idx.reshape(-1).double()).tolist()
+        new = cls(module.bf, cands, module.interp_scale_factor, module.pre_interp)
+        new.load_state_dict(module.state_dict())  # exact float32 buffer
+        new.inv_dist_idx_min, new.inv_dist_idx_max = module.inv_dist_idx_min, module.inv_dist_idx_max
+        return new.to(module.inv_dist_idx.device)
+
+    def update_dist_cands(self, dist_cands: Sequence[float]) -> None:
+        inv_dist_idx = self.bf / torch.tensor(list(dist_cands), dtype=torch.float32)
+        self.inv_dist_idx[:] = inv_dist_idx.view(1, -1, 1, 1).to(dtype=self.inv_dist_idx.dtype,
+                                                                device=self.inv_dist_idx.device)
+        self.inv_dist_idx_min = float(torch.min(self.inv_dist_idx))
+        self.inv_dist_idx_max = float(torch.max(self.inv_dist_idx))
+
+    def _out_size(self, H: int, W: int):
+        if self.pre_interp and self.interp_scale_factor > 0:
+            s = self.interp_scale_factor
+            # F.interpolate(scale_factor=s): floor(size * s); source-index scale = 1/s (recompute_scale_factor unset)
+            return int(math.floor(float(H) * s)), int(math.floor(float(W) * s)), 1.0 / s
+        return H, W, 1.0
+
+    def regress(self, costs: Tensor, want_norm_costs: bool = True, want_argmax: bool = False):
+        _reject_autograd(costs)
+        H, W = costs.shape[-2:]
+        Ho, Wo, scale = self._out_size(H, W)
+        return ops.softargmin_op(costs, self.inv_dist_idx, Ho, Wo, float(scale), want_norm_costs, want_argmax)
+
+    def forward(self, costs: Tensor):
+        """costs [B,1,D,H,W] -> (inv_depths [B,1,sH,sW], norm_costs [B,D,sH,sW])  (reference :51-80)."""
+        inv, nc, _ = self.regress(costs, want_norm_costs=self.return_norm_costs)
+        return inv, (nc if self.return_norm_costs else None)
+
+
+def patch_model(model: nn.Module, rig: Optional[Rig] = None, static_masks: Optional[Tensor] = None,
+                return_norm_costs: bool = True) -> nn.Module:
+    """Swap the reference's cv_builder / dist_regressor of a loaded model for the B200 modules, in place.
+
+    Works on SphericalSweepStereoBase (dsta_mvs/model/mvs_model/torch_only.py:4-35) and on the Lightning wrappers that
+    hold one as `.mvs_model` (spherical_sweep_stereo_2024.py) or hold the four sub-modules directly
+    (spherical_sweep_stereo.py).  Checkpoints keep loading because parameter/buffer names are unchanged."""
+    host = model.mvs_model if hasattr(model, "mvs_model") else model
+    ref_b, ref_r = host.cv_builder, host.dist_regressor
+    kind = type(ref_b).__name__
+    if kind == "SphericalSweepStdMasked":
+        new_b = SphericalSweepStdMasked.from_reference(ref_b)
+    elif kind == "SphericalSweep":
+        new_b = SphericalSweep.from_reference(ref_b)
+    else:
+        raise TypeError(f"cv_builder of type {kind} is not one of the two the reference ships")
+    if rig is not None:
+        new_b.attach_rig(rig)
+    if static_masks is not None:
+        new_b.set_static_masks(static_masks)
+    new_r = DistanceRegressorWithFixedCandidates.from_reference(ref_r)
+    new_r.return_norm_costs = return_norm_costs
+    host.cv_builder, host.dist_regressor = new_b, new_r
+    return model

@@ -1,0 +1,313 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libmvsgi_b200.so (via mvs_gi_b200.ops / modules) and is compared with
+
+  1. the golden vectors generated from the reference's own modules (tests/golden/, oracle/gen_golden.py),
+  2. the CPU oracle (oracle/mvsgi_oracle.c) on seeded inputs the oracle finishes in seconds,
+  3. size-independent properties at BASELINE.json's full sizes.
+
+Pass criteria (SURVEY.md §8c / north_star): validity mask (= zero pattern of vol) and arg-max candidate bit-exact;
+cost volume and inv_dist within 1e-5 * max|ref| in fp32.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # north_star: 1e-5 relative (normalised by max|ref|)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mvs_gi_b200 import abi
+
+    abi.load_library()  # fail loudly if the CUDA extension is missing
+    return torch.device("cuda:0")
+
+
+def t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def relmax(a, ref):
+    return float(np.abs(a - ref).max() / max(float(np.abs(ref).max()), 1e-30))
+
+
+# ------------------------------------------------------------------ 1. golden vectors from the reference modules
+@pytest.mark.parametrize("name", ["std3", "std4"])
+def test_golden_sweep_std(golden, dev, name):
+    from mvs_gi_b200 import modules
+
+    g = golden(f"sweep_{name}")
+    B, CAM, C = g["feats"].shape[:3]
+    m = modules.SphericalSweepStdMasked(CAM, C, 3).to(dev).eval()
+    with torch.no_grad():
+        vol, valid = m.sweep_with_valid(t(g["feats"], dev), t(g["grids"], dev), t(g["grid_masks"], dev),
+                                        t(g["masks"], dev))
+    vol, valid, ref = vol.cpu().numpy(), valid.cpu().numpy(), g["vol"]
+    assert np.array_equal(vol == 0, ref == 0), "zero pattern / validity mask must be bit-exact"
+    assert np.array_equal(np.broadcast_to(valid[:, None], ref.shape), ref != 0)
+    assert relmax(vol, ref) <= TOL
+
+
+def test_golden_sweep_concat(golden, dev):
+    from mvs_gi_b200 import modules
+
+    g = golden("sweep_concat3")
+    B, CAM, C = g["feats"].shape[:3]
+    m = modules.SphericalSweep(CAM, CAM * C, 3).to(dev).eval()
+    with torch.no_grad():
+        vol = m.sweep(t(g["feats"], dev), t(g["grids"], dev), None)
+    assert vol.shape == g["vol"].shape
+    assert relmax(vol.cpu().numpy(), g["vol"]) <= TOL
+
+
+@pytest.mark.parametrize("name", ["sa_d16_s2", "sa_d8_s0", "sa_d8_s2_nopre", "sa_d5_s3"])
+def test_golden_softargmin(golden, dev, name):
+    from mvs_gi_b200 import modules
+
+    g = golden(f"softargmin_{name}")
+    reg = modules.DistanceRegressorWithFixedCandidates(96, list(g["dist"]), float(g["scale"]),
+                                                       bool(g["pre_interp"])).to(dev)
+    assert np.array_equal(reg.inv_dist_idx.cpu().numpy().reshape(-1), g["inv_dist_idx"])
+    with torch.no_grad():
+        inv, nc, am = reg.regress(t(g["costs"], dev), want_norm_costs=True, want_argmax=True)
+        inv2, nc2 = reg(t(g["costs"], dev))
+    assert torch.equal(inv, inv2) and torch.equal(nc, nc2)
+    assert inv.shape == g["inv_dist"].shape and nc.shape == g["norm_costs"].shape
+    assert np.array_equal(am.cpu().numpy(), g["argmax"]), "arg-max candidate must be bit-exact"
+    assert np.array_equal(nc.argmax(1).cpu().numpy(), g["argmax"])
+    assert relmax(inv.cpu().numpy(), g["inv_dist"]) <= TOL
+    assert np.abs(nc.cpu().numpy() - g["norm_costs"]).max() <= TOL
+
+
+# ------------------------------------------------------------------ 2. against the CPU oracle
+def _case(name, B, seed, **small_kw):
+    from mvs_gi_b200 import synthetic
+
+    w = synthetic.small(synthetic.WORKLOADS[name], **small_kw)
+    feats = synthetic.make_feats(w, B, seed)
+    base = synthetic.fisheye_footprint_masks(w)
+    masks = synthetic.erase_rectangles(base, B, seed + 1)
+    return w, feats, base, masks
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("G16V", dict(feat_hw=(32, 128), mask_hw=(128, 512), cv_hw=(20, 80), n_cands=16)),
+    ("4CAM", dict(feat_hw=(32, 128), mask_hw=(128, 512), cv_hw=(20, 80), n_cands=16)),
+    ("G16VV_C48", dict(feat_hw=(16, 64), mask_hw=(64, 256), cv_hw=(10, 40), n_cands=6)),
+    ("G16V_DS", dict(feat_hw=(32, 128), cv_hw=(20, 80), n_cands=5)),
+    ("G16V", dict(feat_hw=(17, 70), mask_hw=(40, 130), cv_hw=(9, 37), n_cands=3)),  # ragged: nothing divides a tile
+])
+def test_fused_projection_vs_oracle(dev, name, kw):
+    """Fused in-kernel projection.  The oracle is fed the kernel's own grids (mvsgi_project_only), so masks are
+    bit-exact by construction of the comparison, and the grids themselves are bounded separately below."""
+    from mvs_gi_b200 import modules, ops
+    from oracle import oracle as orc
+
+    B = 3
+    w, feats, _, masks = _case(name, B, 11, **kw)
+    rig = w.rig()
+    m = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval().attach_rig(rig)
+    with torch.no_grad():
+        vol, valid = m.sweep_with_valid(t(feats, dev), None, None, t(masks, dev))
+        grids, gm = ops.project_only(rig.to_struct(), dev)
+    ref, ref_valid = orc.sweep_std(feats, grids.cpu().numpy()[None], gm.cpu().numpy()[None], masks, return_valid=True)
+    vol = vol.cpu().numpy()
+    assert np.array_equal(valid.cpu().numpy(), ref_valid)
+    assert np.array_equal(vol == 0, ref == 0)
+    assert 0.02 < ref_valid.mean() < 0.999
+    assert relmax(vol, ref) <= TOL
+
+
+@pytest.mark.parametrize("name", ["G16V", "4CAM", "G16V_DS"])
+def test_projection_accuracy(dev, name):
+    """Kernel grids vs the fp32 oracle (reference op order) and vs float64: error no larger than the reference's own
+    distance from float64 (SURVEY.md H2, 1.1e-5 normalised), validity bits equal except ulp-boundary samples."""
+    from mvs_gi_b200 import ops, synthetic
+    from oracle import oracle as orc
+
+    w = synthetic.small(synthetic.WORKLOADS[name], cv_hw=(40, 160))
+    if w.camera == "erp":
+        w.mask_hw = synthetic.WORKLOADS[name].mask_hw
+    rs = w.rig().to_struct()
+    grids, gm = ops.project_only(rs, dev)
+    grids, gm = grids.cpu().numpy(), gm.cpu().numpy()[..., 0]
+    g32, m32 = orc.make_grids(rs)
+    g64, m64 = orc.make_grids_f64(rs)
+    both = gm & m64
+    err64 = np.abs(grids - g64)[both].max()
+    err32 = np.abs(grids - g32)[gm & m32].max()
+    flips = int((gm != m32).sum())
+    print(f"{name}: |kernel-f64|={err64:.2e} |kernel-oracle32|={err32:.2e} flips={flips}/{gm.size}")
+    assert err64 <= 1.1e-5
+    assert flips <= max(2, gm.size // 5000)
+
+
+def test_supplied_grids_vs_oracle_per_frame_everything(dev):
+    """Reference interface: per-frame grids, grid_masks and masks (nothing shared)."""
+    from mvs_gi_b200 import modules
+    from oracle import oracle as orc
+
+    B = 3
+    w, feats, _, masks = _case("G16V", B, 23, feat_hw=(24, 96), mask_hw=(96, 384), cv_hw=(12, 72), n_cands=7)
+    g0, m0 = orc.make_grids(w.rig().to_struct())
+    gen = np.random.default_rng(5)
+    grids = np.repeat(g0[None], B, 0) + gen.normal(0, 0.02, (B, *g0.shape)).astype(np.float32)
+    gmask = np.repeat(m0[None], B, 0) & (gen.random((B, *m0.shape)) > 0.1)
+    m = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval()
+    with torch.no_grad():
+        vol = m.sweep(t(feats, dev), t(grids, dev), t(gmask[..., None], dev), t(masks, dev)).cpu().numpy()
+    ref = orc.sweep_std(feats, grids, gmask, masks)
+    assert np.array_equal(vol == 0, ref == 0)
+    assert relmax(vol, ref) <= TOL
+
+
+def test_layouts_and_sharing_are_equivalent(dev):
+    """NCHW vs channels-last features, bool vs float masks, shared vs replicated masks/grids: identical bits out."""
+    from mvs_gi_b200 import modules
+    from oracle import oracle as orc
+
+    B = 2
+    w, feats, base, _ = _case("G16V", B, 31, feat_hw=(16, 64), mask_hw=(64, 256), cv_hw=(10, 40), n_cands=4)
+    g0, m0 = orc.make_grids(w.rig().to_struct())
+    m = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval()
+    f = t(feats, dev)
+    grids1, gm1, masks1 = t(g0[None], dev), t(m0[None, ..., None], dev), t(base[None], dev)
+    with torch.no_grad():
+        a = m.sweep(f, grids1.expand(B, *grids1.shape[1:]), gm1.expand(B, *gm1.shape[1:]),
+                    masks1.expand(B, *masks1.shape[1:]))
+        b = m.sweep(f, grids1.repeat(B, 1, 1, 1, 1, 1), gm1.repeat(B, 1, 1, 1, 1, 1), masks1.repeat(B, 1, 1, 1, 1))
+        f_cl = f.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)  # channels-last memory, same logical shape
+        assert f_cl.stride(2) == 1
+        c = m.sweep(f_cl, grids1, gm1, masks1)
+        d = m.sweep(f, grids1, gm1, masks1.bool())
+    assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, d)
+    ref = orc.sweep_std(feats, g0[None], m0[None], base[None])
+    assert np.array_equal(a.cpu().numpy() == 0, ref == 0)
+    assert relmax(a.cpu().numpy(), ref) <= TOL
+
+
+def test_concat_vs_oracle_and_edges(dev):
+    from mvs_gi_b200 import modules, synthetic
+    from oracle import oracle as orc
+
+    B = 2
+    w = synthetic.small(synthetic.WORKLOADS["G8"], feat_hw=(16, 64), cv_hw=(10, 40))
+    feats = synthetic.make_feats(w, B, 41)
+    gen = np.random.default_rng(6)
+    grids = gen.uniform(-1.3, 1.3, (B, w.num_cams, w.num_cands, 10, 40, 2)).astype(np.float32)
+    grids[0, 0, 0, 0, :6] = [[-1, -1], [1, 1], [-1 - 1e-6, 0], [0, 1 + 1e-6], [-7, 0.3], [0.1, 9]]
+    grids[0, 1, 0, 0, 0] = [np.nan, 0.0]  # NaN coordinate: zero taps here (documented deviation: reference yields NaN)
+    m = modules.SphericalSweep(w.num_cams, w.out_chs, 3).to(dev).eval()
+    with torch.no_grad():
+        vol = m.sweep(t(feats, dev), t(grids, dev), None).cpu().numpy()
+    grids_o = grids.copy()
+    grids_o[0, 1, 0, 0, 0] = [5.0, 0.0]  # oracle: a far-outside point is also exactly zero
+    ref = orc.sweep_concat(feats, grids_o)
+    assert relmax(vol, ref) <= TOL
+    assert np.all(vol[0, w.feat_chs:2 * w.feat_chs, 0, 0, 0] == 0)
+
+
+@pytest.mark.parametrize("D,scale", [(16, 2), (32, 2), (64, 2), (7, 0), (24, 3)])
+def test_softargmin_vs_oracle(dev, D, scale):
+    """D > 16 uses the warp-shuffle split-D variant."""
+    from mvs_gi_b200 import calibration as cal
+    from mvs_gi_b200 import modules
+    from oracle import oracle as orc
+
+    dist = cal.dist_inverse_spaced(D)
+    gen = np.random.default_rng(D)
+    costs = (gen.standard_normal((2, 1, D, 21, 45)) * 4).astype(np.float32)
+    reg = modules.DistanceRegressorWithFixedCandidates(96, dist, scale, scale > 0).to(dev)
+    with torch.no_grad():
+        inv, nc, am = reg.regress(t(costs, dev), want_norm_costs=True, want_argmax=True)
+    r_inv, r_nc, r_am = orc.softargmin(costs, reg.inv_dist_idx.cpu().numpy(), scale, scale > 0)
+    assert np.array_equal(am.cpu().numpy(), r_am)
+    assert relmax(inv.cpu().numpy(), r_inv) <= TOL
+    assert np.abs(nc.cpu().numpy() - r_nc).max() <= TOL
+
+
+def test_errors_are_loud(dev):
+    from mvs_gi_b200 import modules
+
+    m = modules.SphericalSweepStdMasked(3, 16, 3).to(dev).eval()
+    feats = torch.zeros(1, 3, 16, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.sweep(feats, torch.zeros(1, 3, 2, 4, 4, 2), torch.ones(1, 3, 2, 4, 4, 1, dtype=torch.bool),
+                torch.ones(1, 3, 1, 8, 8))
+    bad = modules.SphericalSweepStdMasked(3, 6, 3).to(dev).eval()
+    with pytest.raises(RuntimeError, match="feat_chs|shape"):
+        bad.sweep(torch.zeros(1, 3, 6, 8, 8, device=dev), torch.zeros(1, 3, 2, 4, 4, 2, device=dev),
+                  torch.ones(1, 3, 2, 4, 4, 1, dtype=torch.bool, device=dev), torch.ones(1, 3, 1, 8, 8, device=dev))
+    with pytest.raises(NotImplementedError):
+        m.sweep(torch.zeros(1, 3, 16, 8, 8, device=dev, requires_grad=True),
+                torch.zeros(1, 3, 2, 4, 4, 2, device=dev),
+                torch.ones(1, 3, 2, 4, 4, 1, dtype=torch.bool, device=dev), torch.ones(1, 3, 1, 8, 8, device=dev))
+
+
+# ------------------------------------------------------------------ 3. full-size properties (BASELINE.json shapes)
+@pytest.mark.parametrize("name,B", [("G16V", 4), ("4CAM", 2), ("HIGHD", 1)])
+def test_full_size_std_properties(dev, name, B):
+    from mvs_gi_b200 import modules, synthetic
+
+    w = synthetic.WORKLOADS[name]
+    rig = w.rig()
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    feats = torch.randn((B, w.num_cams, w.feat_chs, *w.feat_hw), device=dev, generator=gen)
+    masks = t(synthetic.fisheye_footprint_masks(w)[None], dev)
+    m = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval().attach_rig(rig)
+    with torch.no_grad():
+        vol, valid = m.sweep_with_valid(feats, None, None, masks)
+        vol2 = m.sweep(feats * 2.0, None, None, masks)          # variance is homogeneous of degree 2: x4, exactly
+        perm = torch.randperm(B, device=dev)
+        vol_p = m.sweep(feats[perm], None, None, masks)          # frames are independent
+        vol_c = m.sweep(feats + 3.0, None, None, masks)          # variance is shift invariant (up to rounding)
+    assert vol.shape == (B, w.feat_chs, w.num_cands, *w.cv_hw)
+    assert torch.isfinite(vol).all() and (vol >= 0).all()
+    assert torch.equal(vol != 0, valid[:, None].expand_as(vol)), "zero pattern == validity mask"
+    assert 0.2 < valid.float().mean().item() < 0.999
+    assert torch.equal(vol2, vol * 4.0)
+    assert torch.equal(vol_p, vol[perm])
+    assert (vol_c - vol).abs().max().item() <= 2e-5 * vol.abs().max().item() * 10
+    # validity is independent of the frame when masks/geometry are shared
+    assert torch.equal(valid, valid[:1].expand_as(valid))
+
+
+def test_full_size_concat_linearity(dev):
+    from mvs_gi_b200 import modules, synthetic
+
+    w = synthetic.WORKLOADS["G8"]
+    B = 4
+    gen = torch.Generator(device=dev).manual_seed(7)
+    f1 = torch.randn((B, w.num_cams, w.feat_chs, *w.feat_hw), device=dev, generator=gen)
+    f2 = torch.randn((B, w.num_cams, w.feat_chs, *w.feat_hw), device=dev, generator=gen)
+    m = modules.SphericalSweep(w.num_cams, w.out_chs, 3).to(dev).eval().attach_rig(w.rig())
+    with torch.no_grad():
+        v1, v2 = m.sweep(f1, None), m.sweep(f2, None)
+        v12 = m.sweep(f1 * 2.0 + f2, None)
+    assert v1.shape == (B, 48, 8, 80, 320)
+    assert (v12 - (2.0 * v1 + v2)).abs().max().item() <= 1e-5 * v12.abs().max().item()
+    assert torch.equal(m.sweep(f1 * 0.5, None), v1 * 0.5)
+
+
+def test_full_size_softargmin_properties(dev):
+    from mvs_gi_b200 import calibration as cal
+    from mvs_gi_b200 import modules
+
+    B, D = 8, 16
+    gen = torch.Generator(device=dev).manual_seed(99)
+    costs = torch.randn((B, 1, D, 80, 320), device=dev, generator=gen) * 3
+    reg = modules.DistanceRegressorWithFixedCandidates(96, cal.DIST_16CPD, 2, True).to(dev)
+    with torch.no_grad():
+        inv, nc, am = reg.regress(costs, want_norm_costs=True, want_argmax=True)
+        up = torch.nn.functional.interpolate(costs[:, 0].cpu(), scale_factor=2, mode="bilinear")
+    assert inv.shape == (B, 1, 160, 640) and nc.shape == (B, D, 160, 640)
+    assert (nc.sum(1) - 1).abs().max().item() <= 1e-5
+    assert inv.min().item() >= reg.inv_dist_idx_min * (1 - 1e-6) and inv.max().item() <= reg.inv_dist_idx_max * (1 + 1e-6)
+    assert torch.equal(am.cpu().long(), up.argmax(1)), "arg-max candidate vs PyTorch CPU upsample: bit-exact"
+    assert torch.equal(nc.argmax(1).cpu(), up.argmax(1))
+    ref_inv = (torch.softmax(up, 1) * reg.inv_dist_idx.cpu()).sum(1, keepdim=True)
+    assert (inv.cpu() - ref_inv).abs().max().item() <= TOL * ref_inv.abs().max().item()

@@ -103,3 +103,20 @@ def test_geometry(golden, name):
     assert err_oracle_f64 <= max(2 * err_ref_f64, 2e-5)
     assert flips <= max(2, gm.size // 5000), "validity may only differ on ulp-boundary samples"
     assert int((gm64 != ref_m).sum()) <= max(2, gm.size // 5000)
+
+
+# ---- the PyTorch-eager port that is timed as the CPU baseline must agree with the reference vectors too
+def test_torch_port_matches_golden(golden):
+    import torch
+
+    from oracle import ref_port_torch as port
+
+    g = golden("sweep_std3")
+    vol = port.sweep_std(*(torch.from_numpy(g[k]) for k in ("feats", "grids", "grid_masks", "masks")))
+    assert np.array_equal(vol.numpy(), g["vol"])
+    g = golden("sweep_concat3")
+    vol = port.sweep_concat(torch.from_numpy(g["feats"]), torch.from_numpy(g["grids"]))
+    assert np.array_equal(vol.numpy(), g["vol"])
+    g = golden("softargmin_sa_d16_s2")
+    inv, nc = port.soft_argmin(torch.from_numpy(g["costs"]), torch.from_numpy(g["inv_dist_idx"]), 2, True)
+    assert np.array_equal(inv.numpy(), g["inv_dist"]) and np.array_equal(nc.numpy(), g["norm_costs"])
