@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "softargmin.cuh"
+#include "stage.cuh"
 #include "sweep.cuh"
 
 namespace {
@@ -20,29 +21,25 @@ int env_int(const char* name, int dflt) {
 }
 
 struct SweepPlan {
-  bool stage_feats;       // feats are not channels-last: transpose into the workspace first
   bool pack_masks;        // std builder: masks -> bit images
   bool per_frame_masks;
   bool per_frame_grids;
   int n_mask_images;      // B*CAM or CAM
-  int mask_pitch;
+  int mask_pitch, mask_words;
+  int cg;                 // 16-channel groups of the staged features
   int64_t feats_bytes, mask_bytes, flag_bytes, total_bytes;
-  int tile_h, dch, num_chunks, tiles_x, tiles_y;
+  int dch, num_chunks, num_runs, run_len, num_items, max_pairs, grid, group_px;
   size_t smem_bytes;
   int cout;
 };
 
 int mask_pitch_words(int mask_w) { return (mask_w + 2 + 31) / 32 + 1; }
 
-bool is_channels_last(const MvsgiSweepArgs* a) {
-  const int64_t* s = a->feats_stride;  // B, CAM, C, H, W
-  if (s[2] != 1) return false;
-  if ((reinterpret_cast<uintptr_t>(a->feats) & 15) != 0) return false;
-  for (int i : {0, 1, 3, 4})
-    if (s[i] % 4 != 0) return false;
-  // in-image offsets are kept in int32
-  if (s[3] * a->feat_h >= (1ll << 31) || s[4] * a->feat_w >= (1ll << 31)) return false;
-  return true;
+int device_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+  return sms;
 }
 
 int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
@@ -56,9 +53,13 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   if (a->batch <= 0 || a->feat_chs <= 0 || a->out_h <= 0 || a->out_w <= 0) return MVSGI_E_SHAPE;
   if (a->num_cams < 1 || a->num_cams > MVSGI_MAX_CAMS) return MVSGI_E_SHAPE;
   if (a->num_cands < 1) return MVSGI_E_SHAPE;
-  if (a->feat_h < 2 || a->feat_w < 2) return MVSGI_E_SHAPE;
-  if (a->feat_chs % 4 != 0) return MVSGI_E_SHAPE;  // 16-byte taps
+  if (a->feat_h < 1 || a->feat_w < 1) return MVSGI_E_SHAPE;
   if (a->feats == nullptr || a->vol == nullptr) return MVSGI_E_NULL;
+  // in-image tap offsets and in-frame output offsets are kept in int32
+  const int64_t cg64 = (a->feat_chs + mvsgi::kCG - 1) / mvsgi::kCG;
+  if ((int64_t)a->num_cams * cg64 * (a->feat_h + 3) * (a->feat_w + 2) * mvsgi::kCG >= (1ll << 31)) return MVSGI_E_SHAPE;
+  const int64_t cout64 = (int64_t)a->feat_chs * (a->aggregate == MVSGI_AGG_CONCAT ? a->num_cams : 1);
+  if (cout64 * a->num_cands * a->out_h * a->out_w >= (1ll << 31)) return MVSGI_E_SHAPE;
   const bool std_agg = a->aggregate == MVSGI_AGG_STD;
   if (std_agg) {
     if (a->masks == nullptr) return MVSGI_E_NULL;
@@ -82,70 +83,81 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   }
 
   p->cout = std_agg ? a->feat_chs : a->feat_chs * a->num_cams;
-  p->stage_feats = !is_channels_last(a);
+  p->cg = (a->feat_chs + mvsgi::kCG - 1) / mvsgi::kCG;
   p->pack_masks = std_agg;
   p->per_frame_masks = std_agg && a->batch > 1 && a->masks_stride[0] != 0;
   p->per_frame_grids = a->grid_mode == MVSGI_GRID_SUPPLIED && a->batch > 1 &&
                        (a->grids_stride[0] != 0 || (std_agg && a->grid_masks_stride[0] != 0));
   p->n_mask_images = std_agg ? (p->per_frame_masks ? a->batch : 1) * a->num_cams : 0;
   p->mask_pitch = std_agg ? mask_pitch_words(a->mask_w) : 0;
-  p->feats_bytes =
-      p->stage_feats ? align_up((int64_t)a->batch * a->num_cams * a->feat_h * a->feat_w * a->feat_chs * 4, 256) : 0;
-  p->mask_bytes = align_up((int64_t)p->n_mask_images * (a->mask_h + 2) * p->mask_pitch * 4, 256);
+  p->mask_words = std_agg ? (a->mask_h + 2) * p->mask_pitch : 0;
+  p->feats_bytes = align_up((int64_t)a->batch * a->num_cams * p->cg * (a->feat_h + 3) * (a->feat_w + 2) * mvsgi::kCG * 4, 256);
+  p->mask_bytes = align_up((int64_t)p->n_mask_images * p->mask_words * 4 + 16, 256);  // +16: funnel-shift over-read
   p->flag_bytes = 256;
   p->total_bytes = p->feats_bytes + p->mask_bytes + p->flag_bytes;
 
-  // tile / candidate-chunk shape: 2 x 32 pixels, up to 16 candidates per chunk, table capped at ~64 KB so that two
-  // CTAs per SM still leave >= 96 KB of the 228 KB unified array as L1 for the gathers.
-  p->tile_h = env_int("MVSGI_TILE_H", 2);
-  if (p->tile_h != 1 && p->tile_h != 2 && p->tile_h != 4) p->tile_h = 2;
-  const int tp = p->tile_h * mvsgi::kTileW;
-  const int bytes_per_ent = 20 + (p->per_frame_masks ? 4 : 0);
+  // Work decomposition (sweep.cuh): equal runs of output pixels, one per resident CTA when the tap table fits.
+  const int P = a->out_h * a->out_w;
+  int ctas_per_sm = env_int("MVSGI_CTAS_PER_SM", 2);
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 2) ctas_per_sm = 2;  // __launch_bounds__(512, 2)
+  const int grid_target = device_sms() * ctas_per_sm;
   int dch = env_int("MVSGI_DCH", 16);
   if (dch < 1) dch = 1;
   if (dch > a->num_cands) dch = a->num_cands;
-  const int budget = env_int("MVSGI_TABLE_BYTES", 64 * 1024);
-  while (dch > 1 && (int64_t)dch * a->num_cams * tp * bytes_per_ent > budget) dch = (dch + 1) / 2;
+  const bool std_tab = std_agg;
+  const int64_t per_pair = (int64_t)mvsgi::entry_words(a->num_cams) * 4 + (std_tab ? a->num_cams * 4 : 0);
+  const int64_t per_px = (int64_t)dch * per_pair + 12;
+  const int64_t budget = env_int("MVSGI_TABLE_BYTES", ctas_per_sm == 2 ? 80 * 1024 : 160 * 1024);
+  const int num_oct = (P + 7) / 8;
+  int run_oct = (num_oct + grid_target - 1) / grid_target;
+  if ((int64_t)run_oct * 8 * per_px > budget) run_oct = (int)(budget / (8 * per_px));
+  if (run_oct < 1) return MVSGI_E_SHAPE;
+  p->num_runs = (num_oct + run_oct - 1) / run_oct;
+  p->run_len = 8 * ((num_oct + p->num_runs - 1) / p->num_runs);
   p->dch = dch;
   p->num_chunks = (a->num_cands + dch - 1) / dch;
-  p->tiles_x = (a->out_w + mvsgi::kTileW - 1) / mvsgi::kTileW;
-  p->tiles_y = (a->out_h + p->tile_h - 1) / p->tile_h;
-  p->smem_bytes = (size_t)dch * a->num_cams * tp * bytes_per_ent + (size_t)dch * tp + 16;
+  p->num_items = p->num_runs * p->num_chunks;
+  p->max_pairs = p->run_len * dch;
+  p->grid = p->num_items < grid_target ? p->num_items : grid_target;
+  p->group_px = env_int("MVSGI_GROUP_PX", 32);
+  if (p->group_px < 1) p->group_px = 1;
+  p->smem_bytes = align_up((int64_t)p->max_pairs * per_pair + (int64_t)p->run_len * 12 + 16, 16);
   return MVSGI_OK;
 }
 
 template <int CAM, int AGG>
-cudaError_t launch_sweep(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, int threads, size_t smem,
-                         cudaStream_t st) {
+cudaError_t launch_sweep(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
   auto kern = mvsgi::sweep_kernel<CAM, AGG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, threads, smem, st>>>(kp, rig);
+  kern<<<grid, mvsgi::kSweepThreads, smem, st>>>(kp, rig);
   g_launches++;
   return cudaGetLastError();
 }
 
 template <int AGG>
-cudaError_t dispatch_cams(int cams, const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, int threads, size_t smem,
+cudaError_t dispatch_cams(int cams, const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
                           cudaStream_t st) {
   switch (cams) {
-    case 1: return launch_sweep<1, AGG>(kp, rig, grid, threads, smem, st);
-    case 2: return launch_sweep<2, AGG>(kp, rig, grid, threads, smem, st);
-    case 3: return launch_sweep<3, AGG>(kp, rig, grid, threads, smem, st);
-    default: return launch_sweep<4, AGG>(kp, rig, grid, threads, smem, st);
+    case 1: return launch_sweep<1, AGG>(kp, rig, grid, smem, st);
+    case 2: return launch_sweep<2, AGG>(kp, rig, grid, smem, st);
+    case 3: return launch_sweep<3, AGG>(kp, rig, grid, smem, st);
+    default: return launch_sweep<4, AGG>(kp, rig, grid, smem, st);
   }
 }
 
 cudaError_t launch_pack(const void* masks, int dtype, int n0, int64_t s0, int n1, int64_t s1, int64_t sh, int64_t sw,
                         int Hm, int Wm, uint32_t* bits, int* flags, cudaStream_t st) {
   const int pitch = mask_pitch_words(Wm);
-  dim3 grid((pitch + 7) / 8, Hm + 2, n0 * n1);
+  const int words = (Hm + 2) * pitch;
+  dim3 grid((words + 63) / 64, n0 * n1);
   if (dtype == MVSGI_MASK_F32)
-    mvsgi::pack_masks_kernel<float><<<grid, 256, 0, st>>>((const float*)masks, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits,
-                                                          flags);
+    mvsgi::pack_masks_kernel<float><<<grid, 256, 0, st>>>((const float*)masks, n1, s0, s1, sh, sw, Hm, Wm, pitch, words,
+                                                          bits, flags);
   else
     mvsgi::pack_masks_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)masks, n1, s0, s1, sh, sw, Hm, Wm, pitch,
-                                                            bits, flags);
+                                                            words, bits, flags);
   g_launches++;
   return cudaGetLastError();
 }
@@ -183,7 +195,7 @@ int mvsgi_sweep_launch_count(const MvsgiSweepArgs* a) {
   SweepPlan p;
   const int rc = validate_and_plan(a, &p);
   if (rc != MVSGI_OK) return rc;
-  const int stage = (p.stage_feats ? 1 : 0) + (p.pack_masks ? 1 : 0);
+  const int stage = 1 + (p.pack_masks ? 1 : 0);
   if (a->flags & MVSGI_FLAG_STAGE_ONLY) return stage;
   if (a->flags & MVSGI_FLAG_SWEEP_ONLY) return 1;
   return 1 + stage;
@@ -203,11 +215,9 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
   SweepPlan p;
   int rc = validate_and_plan(a, &p);
   if (rc != MVSGI_OK) return rc;
-  if (p.total_bytes > 0) {
-    if (a->workspace == nullptr) return MVSGI_E_NULL;
-    if (a->workspace_bytes < p.total_bytes || (reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0)
-      return MVSGI_E_WORKSPACE;
-  }
+  if (a->workspace == nullptr) return MVSGI_E_NULL;
+  if (a->workspace_bytes < p.total_bytes || (reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0)
+    return MVSGI_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)a->workspace;
   float* ws_feats = (float*)ws;
@@ -216,57 +226,53 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
   const bool std_agg = a->aggregate == MVSGI_AGG_STD;
   const bool do_stage = !(a->flags & MVSGI_FLAG_SWEEP_ONLY);
   const bool do_sweep = !(a->flags & MVSGI_FLAG_STAGE_ONLY);
+  const int Wp = a->feat_w + 2, Hp1 = a->feat_h + 3;
 
-  mvsgi::SweepKP kp;
-  memset(&kp, 0, sizeof(kp));
-  kp.B = a->batch; kp.C = a->feat_chs; kp.D = a->num_cands; kp.Cout = p.cout;
-  kp.Ho = a->out_h; kp.Wo = a->out_w; kp.Hf = a->feat_h; kp.Wf = a->feat_w; kp.Hm = a->mask_h; kp.Wm = a->mask_w;
-  kp.tileH = p.tile_h; kp.dch = p.dch; kp.numChunks = p.num_chunks; kp.tilesX = p.tiles_x;
-  kp.numTiles = p.tiles_x * p.tiles_y;
-  kp.totalItems = (long long)kp.numTiles * p.num_chunks * a->batch;
-
-  // 1. features -> channels-last
-  if (p.stage_feats) {
+  // 1. features -> zero-padded channel-group-major channels-last
+  if (do_stage) {
     const int N = a->batch * a->num_cams;
-    dim3 grid((a->feat_w + 31) / 32, a->feat_h, N);
-    const size_t smem = (size_t)a->feat_chs * 33 * sizeof(float);
-    if (smem > 48 * 1024) return MVSGI_E_SHAPE;
-    if (do_stage) {
-      mvsgi::nhwc_stage_kernel<<<grid, 256, smem, st>>>(a->feats, a->feats_stride[0], a->num_cams, a->feats_stride[1],
-                                                        a->feats_stride[2], a->feats_stride[3], a->feats_stride[4],
-                                                        a->feat_chs, a->feat_h, a->feat_w, ws_feats);
-      g_launches++;
-      cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) return (int)e;
-    }
-    kp.feat = ws_feats;
-    kp.fsX = a->feat_chs;
-    kp.fsY = a->feat_w * a->feat_chs;
-    kp.fsCam = (long long)a->feat_h * kp.fsY;
-    kp.fsB = kp.fsCam * a->num_cams;
-  } else {
-    kp.feat = a->feats;
-    kp.fsB = a->feats_stride[0]; kp.fsCam = a->feats_stride[1];
-    kp.fsY = (int)a->feats_stride[3]; kp.fsX = (int)a->feats_stride[4];
+    const int x_blocks = (Wp + mvsgi::kStagePx - 1) / mvsgi::kStagePx;
+    if ((int64_t)N * p.cg * x_blocks >= (1ll << 31) || Hp1 > 65535) return MVSGI_E_SHAPE;
+    dim3 grid((unsigned)(N * p.cg * x_blocks), Hp1);
+    const int chan_fastest = (a->feats_stride[2] == 1 && a->feats_stride[4] != 1) ? 1 : 0;
+    mvsgi::stage_feats_kernel<<<grid, 256, 0, st>>>(a->feats, a->feats_stride[0], a->num_cams, a->feats_stride[1],
+                                                    a->feats_stride[2], a->feats_stride[3], a->feats_stride[4],
+                                                    a->feat_chs, p.cg, a->feat_h, a->feat_w, x_blocks, chan_fastest,
+                                                    ws_feats);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
   }
 
   // 2. masks -> bits
-  if (p.pack_masks) {
-    if (do_stage) {
-      cudaError_t e = launch_pack(a->masks, a->masks_dtype, p.per_frame_masks ? a->batch : 1, a->masks_stride[0],
-                                  a->num_cams, a->masks_stride[1], a->masks_stride[2], a->masks_stride[3], a->mask_h,
-                                  a->mask_w, ws_bits, ws_flags, st);
-      if (e != cudaSuccess) return (int)e;
-    }
-    kp.mbits = ws_bits;
-    kp.mPitch = p.mask_pitch;
-    kp.mbCam = (long long)(a->mask_h + 2) * p.mask_pitch;
-    kp.mbB = kp.mbCam * a->num_cams;
-    kp.perFrameMasks = p.per_frame_masks ? 1 : 0;
+  if (p.pack_masks && do_stage) {
+    cudaError_t e = launch_pack(a->masks, a->masks_dtype, p.per_frame_masks ? a->batch : 1, a->masks_stride[0],
+                                a->num_cams, a->masks_stride[1], a->masks_stride[2], a->masks_stride[3], a->mask_h,
+                                a->mask_w, ws_bits, ws_flags, st);
+    if (e != cudaSuccess) return (int)e;
   }
 
   // 3. the sweep
   if (!do_sweep) return MVSGI_OK;
+  mvsgi::SweepKP kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.B = a->batch; kp.C = a->feat_chs; kp.D = a->num_cands; kp.Cout = p.cout; kp.CG = p.cg;
+  kp.Ho = a->out_h; kp.Wo = a->out_w; kp.Hf = a->feat_h; kp.Wf = a->feat_w; kp.Hm = a->mask_h; kp.Wm = a->mask_w;
+  kp.P = a->out_h * a->out_w; kp.numRuns = p.num_runs; kp.runLen = p.run_len; kp.dch = p.dch;
+  kp.numChunks = p.num_chunks; kp.numItems = p.num_items; kp.maxPairs = p.max_pairs; kp.grpPx = p.group_px;
+  kp.feat = ws_feats;
+  kp.fsY = Wp * mvsgi::kCG;
+  kp.fsCg = Hp1 * kp.fsY;
+  kp.fsCam = kp.fsCg * p.cg;
+  kp.fsB = (long long)kp.fsCam * a->num_cams;
+  kp.zeroOff = (a->feat_h + 1) * kp.fsY;  // rows Hf+1 and Hf+2 are all zero
+  if (p.pack_masks) {
+    kp.mbits = ws_bits;
+    kp.mPitch = p.mask_pitch;
+    kp.mbCam = p.mask_words;
+    kp.mbB = kp.mbCam * a->num_cams;
+    kp.perFrameMasks = p.per_frame_masks ? 1 : 0;
+  }
   kp.gridMode = a->grid_mode;
   kp.perFrameGrids = p.per_frame_grids ? 1 : 0;
   if (a->grid_mode == MVSGI_GRID_SUPPLIED) {
@@ -286,22 +292,8 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
   if (a->grid_mode == MVSGI_GRID_PROJECT) rig = *a->rig;
   else memset(&rig, 0, sizeof(rig));
 
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int threads = p.tile_h * mvsgi::kTileW * mvsgi::kLanesPerPixel;
-  int ctas_per_sm = env_int("MVSGI_CTAS_PER_SM", 0);
-  if (ctas_per_sm <= 0) {
-    ctas_per_sm = (int)((200 * 1024) / (p.smem_bytes + 1024));
-    const int by_threads = 1536 / threads;  // leave the rest of the 228 KB array to L1
-    if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
-    if (ctas_per_sm > 2) ctas_per_sm = 2;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-  }
-  long long grid = (long long)sms * ctas_per_sm;
-  if (grid > kp.totalItems) grid = kp.totalItems;
-  cudaError_t e = std_agg ? dispatch_cams<MVSGI_AGG_STD>(a->num_cams, kp, rig, (int)grid, threads, p.smem_bytes, st)
-                          : dispatch_cams<MVSGI_AGG_CONCAT>(a->num_cams, kp, rig, (int)grid, threads, p.smem_bytes, st);
+  cudaError_t e = std_agg ? dispatch_cams<MVSGI_AGG_STD>(a->num_cams, kp, rig, p.grid, p.smem_bytes, st)
+                          : dispatch_cams<MVSGI_AGG_CONCAT>(a->num_cams, kp, rig, p.grid, p.smem_bytes, st);
   return (int)e;
 }
 

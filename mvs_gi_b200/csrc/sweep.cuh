@@ -6,44 +6,51 @@
 //   dsta_mvs/model/cost_volume_builder/spherical_sweep.py:38-68       (concat)
 //   dsta_mvs/model/backports/backports.py:11-86                       (bilinear_grid_sample)
 //
+// Data layout (produced by stage.cuh): features are staged once per call into zero-padded, channel-group-major,
+// channels-last images  [B][CAM][CG][Hf+3][Wf+2][16]  (fp32).  The one-pixel zero frame IS the reference's F.pad
+// (backports.py:58), so a bilinear sample is always four unconditional taps; the extra all-zero row at the bottom gives
+// far-outside samples an all-zero 2x2 patch to read.  Two horizontally adjacent pixels of a 16-channel group are
+// 128 contiguous bytes.
+//
 // Work decomposition
-//   item  = (output tile of tileH x 32 pixels, chunk of `dch` candidates, frame b)
-//   CTA   = persistent; owns a contiguous range of items ordered (tile, chunk, frame) so that
-//           consecutive items share their geometry.
-//   phase 1  (once per (tile, chunk) when grids are batch-shared / projected in-kernel; once per item otherwise):
-//           evaluate or load the sampling grid and turn it into a *tap table* in shared memory:
-//           per (candidate, camera, pixel) one int32 element offset of the top-left tap plus the four
-//           bilinear weights, zero-padding already folded in (out-of-image taps get weight 0 and an
-//           in-bounds address).  The std builder also resolves the mask test there into 1 bit per camera.
-//   phase 2  4 lanes per output pixel, lane q owns channels [4q, 4q+4) of the current 16-channel group:
-//           every tap is one 16-byte load from the channels-last feature map (4 lanes = 64 contiguous bytes
-//           per pixel); the candidate loop runs innermost so the sliding per-camera footprint of the tile
-//           stays in L1 from one candidate to the next; mean/variance across cameras happens in
-//           registers; per-view warped volumes are never materialised; the (C, D, H, W) volume is written
-//           once with streaming stores, 8 consecutive pixels = one full 32-byte sector per warp per channel.
+//   run   = a contiguous range of output pixels in row-major (h, w) order; every CTA owns the same number of pixels.
+//   item  = (run, chunk of <= dch candidates).  With the default plan there is exactly one item per CTA.
+//   build = once per item (once per frame only when the caller supplies per-frame grids): evaluate the projection
+//           (geometry.cuh) or read the supplied grid and turn it into a *tap table* in shared memory — per
+//           (camera, candidate, pixel) the tap offset, frac x, frac y and the mask lookup info (16 bytes in all).
+//   masks = once per item when masks are shared by all frames, else once per frame: a coalesced pass turns the mask
+//           lookup info into one validity byte per (candidate, pixel).
+//   sweep = frames OUTER, so all CTAs walk the batch together and one frame's features (12.6 MB at G16V) are read
+//           from HBM once and then served by the 126 MB L2.  Inside a frame a quad of 4 lanes owns one
+//           (pixel, candidate) pair; pairs are ordered pixel-group-major / candidate / pixel so that the sliding
+//           footprint of ~32 pixels x all candidates stays in L1.
+//           Per camera and per tap row the quad issues ONE 256-bit load per lane: 4 lanes x 32 B = the 128 contiguous
+//           bytes of taps (x0, x0+1) x 16 channels, so a warp-wide request touches every 128-byte line once (half the
+//           L1 wavefronts of separate x0 / x1 requests).  Rows are blended first, the two pixel halves are exchanged
+//           with 4 quad shuffles, and each lane ends up with 4 channels of the sample.  Mean / variance across the
+//           cameras happens in registers; per-view warped volumes are never materialised; the (C, D, H, W) volume
+//           is written once with streaming stores.
 #pragma once
 #include "geometry.cuh"
 
 namespace mvsgi {
 
-constexpr int kTileW = 32;          // output pixels per tile row
-constexpr int kLanesPerPixel = 4;   // 4 lanes x float4 = 16 channels
+constexpr int kCG = 16;             // channels per staged channel group
+constexpr int kSweepThreads = 512;  // 128 quads per CTA
 constexpr uint32_t kMaskNone = 0xFFFFFFFFu;
 
 struct SweepKP {
-  int B, C, D, Cout;
+  int B, C, D, Cout, CG;
   int Ho, Wo, Hf, Wf, Hm, Wm;
-  int tileH, dch, numChunks, tilesX, numTiles;
-  long long totalItems;
-  // channels-last feature view: element (b, cam, y, x, c) at feat[b*fsB + cam*fsCam + y*fsY + x*fsX + c]
+  int P, numRuns, runLen, dch, numChunks, numItems, maxPairs, grpPx;
+  // staged features: element (b, cam, cg, yp, xp, c) at feat[b*fsB + cam*fsCam + cg*fsCg + yp*fsY + xp*16 + c]
   const float* feat;
-  long long fsB, fsCam;
-  int fsY, fsX;
+  long long fsB;
+  int fsCam, fsCg, fsY, zeroOff;  // host checks CAM * fsCam < 2^31
   // packed masks (std): uint32 words, image (b, cam) at mbits + b*mbB + cam*mbCam, (Hm+2) rows of mPitch words
   const uint32_t* mbits;
   long long mbB, mbCam;
-  int mPitch;
-  int perFrameMasks;
+  int mPitch, perFrameMasks;
   // supplied grids: (b, cam, d, h, w) -> 2 floats ; grid_masks -> 1 byte
   int gridMode, perFrameGrids;
   const float* grids;
@@ -54,47 +61,18 @@ struct SweepKP {
   uint8_t* validOut;
 };
 
-// ---- tap table entry --------------------------------------------------------------------------------------------
-struct TapEntry {
-  int off;             // element offset of tap (y_base, x_base) inside one (b, cam) feature image
-  float wa, wb, wc, wd;  // weights of (y_base,x_base), (y_base+1,x_base), (y_base,x_base+1), (y_base+1,x_base+1)
+struct __align__(32) F8 {
+  float v[8];
 };
 
-// One axis of bilinear_grid_sample with zero padding folded in.
-//   v       continuous pixel coordinate (backports.py:41-42)
-//   base    first of the two in-bounds pixels actually read
-//   w0, w1  weights of pixel base and base+1  (== (x1-x), (x-x0) of backports.py:52-55 when both are in bounds)
-MVSGI_DEV void axis_taps(float v, int size, int& base, float& w0, float& w1) {
-  const float f0 = floorf(v);
-  base = 0;
-  w0 = 0.0f;
-  w1 = 0.0f;
-  // also rejects NaN; taps entirely in the zero padding contribute exactly 0 (backports.py:58-72)
-  if (!(v >= -1.0f && v < (float)size)) return;
-  const int i0 = (int)f0;
-  const float hi = fsub(fadd(f0, 1.0f), v);  // (x1 - x)
-  const float lo = fsub(v, f0);              // (x - x0)
-  if (i0 < 0) {               // x0 = -1 is padding, x1 = 0 is pixel 0
-    base = 0; w0 = lo; w1 = 0.0f;
-  } else if (i0 >= size - 1) {  // x0 = size-1 is the last pixel, x1 is padding
-    base = size - 2; w0 = 0.0f; w1 = hi;
-  } else {
-    base = i0; w0 = hi; w1 = lo;
-  }
-}
-
-MVSGI_DEV TapEntry make_tap_entry(float gx, float gy, int Hf, int Wf, int fsY, int fsX) {
-  int bx, by;
-  float cw0, cw1, rw0, rw1;
-  axis_taps(unnormalise(gx, Wf), Wf, bx, cw0, cw1);
-  axis_taps(unnormalise(gy, Hf), Hf, by, rw0, rw1);
-  TapEntry e;
-  e.off = by * fsY + bx * fsX;
-  e.wa = fmul(cw0, rw0);
-  e.wb = fmul(cw0, rw1);
-  e.wc = fmul(cw1, rw0);
-  e.wd = fmul(cw1, rw1);
-  return e;
+// 32 contiguous bytes per lane through the read-only path (LDG.E.256 on sm_100a).
+MVSGI_DEV F8 ldg256(const float* p) {
+  F8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
+                 "=f"(r.v[7])
+               : "l"(p));
+  return r;
 }
 
 // Mask test of spherical_sweep_avg.py:92-96 for 0/1 (non-negative) masks: bilinear(mask) > 0  <=>  some tap has
@@ -128,193 +106,236 @@ MVSGI_DEV bool mask_lookup(const uint32_t* __restrict__ img, uint32_t info, int 
   return (hit & 1u) != 0;
 }
 
-MVSGI_DEV float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
-MVSGI_DEV float4 bilerp(const float4 a, const float4 b, const float4 c, const float4 d, float wa, float wb, float wc,
-                        float wd) {
-  // backports.py:86  Ia*wa + Ib*wb + Ic*wc + Id*wd (left to right; contraction into FMAs allowed)
-  float4 r;
-  r.x = fmaf(d.x, wd, fmaf(c.x, wc, fmaf(b.x, wb, a.x * wa)));
-  r.y = fmaf(d.y, wd, fmaf(c.y, wc, fmaf(b.y, wb, a.y * wa)));
-  r.z = fmaf(d.z, wd, fmaf(c.z, wc, fmaf(b.z, wb, a.z * wa)));
-  r.w = fmaf(d.w, wd, fmaf(c.w, wc, fmaf(b.w, wb, a.w * wa)));
-  return r;
+// Tap-table entry of one (camera, candidate, pixel): element offset of tap (y0, x0) inside a staged (b, cam, cg)
+// image, frac x (x - x0) and frac y.  backports.py:41-55 with the zero padding folded into the staged image; samples
+// whose four taps all fall into the padding (and NaN coordinates) read the all-zero patch.
+MVSGI_DEV void make_entry(const SweepKP& kp, float gx, float gy, int& off, float& lx, float& ly) {
+  const float x = unnormalise(gx, kp.Wf), y = unnormalise(gy, kp.Hf);
+  if (!(x >= -1.0f && x < (float)kp.Wf && y >= -1.0f && y < (float)kp.Hf)) {
+    off = kp.zeroOff;
+    lx = 0.0f;
+    ly = 0.0f;
+  } else {
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    off = ((int)fy0 + 1) * kp.fsY + ((int)fx0 + 1) * kCG;
+    lx = fsub(x, fx0);
+    ly = fsub(y, fy0);
+  }
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
+// Shared-memory tap table: one record of kEntryWords(CAM) words per (candidate, pixel) pair
+//   [0] output offset d*Ho*Wo + h*Wo + w   [1] validity bits of the cameras (rewritten per frame if masks are per frame)
+//   [2+3c .. 4+3c] camera c: tap offset, frac x, frac y
+// The record stride is odd, so the 8 records a warp reads at a time sit in 8 different banks.
+__host__ __device__ constexpr int entry_words(int cam) { return (2 + 3 * cam) | 1; }
+
 template <int CAM, int AGG>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(kSweepThreads, 2)
 sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int TP = kp.tileH * kTileW;            // pixels per tile
-  const int nEnt = kp.dch * CAM * TP;          // tap-table entries
-  int* tOff = reinterpret_cast<int*>(smem_raw);
-  float* tW = reinterpret_cast<float*>(tOff + nEnt);       // 4 planes of nEnt
-  uint32_t* tM = reinterpret_cast<uint32_t*>(tW + 4 * nEnt);  // only when masks are per frame
-  unsigned char* vb = reinterpret_cast<unsigned char*>(tM + (kp.perFrameMasks ? nEnt : 0));  // dch * TP
+  constexpr int ES = entry_words(CAM);
+  const int MP = kp.maxPairs;
+  uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw);             // [MP][ES]
+  float* rays = reinterpret_cast<float*>(tab + (size_t)MP * ES);     // [runLen][3]
+  uint32_t* tMi = reinterpret_cast<uint32_t*>(rays + 3 * kp.runLen);  // [CAM][MP] mask lookup info (std only)
 
-  const int tid = threadIdx.x;
-  // phase-1 mapping: one pixel per thread, candidates strided over the 4 thread groups
-  const int p1 = tid % TP, g1 = tid / TP;
-  // phase-2 mapping: 4 lanes per pixel
-  const int p2 = tid >> 2, q = tid & 3;
+  const int tid = threadIdx.x, lane = tid & 31, q = lane & 3;
+  const int warp = tid >> 5;
+  constexpr int nwarps = kSweepThreads >> 5;
+  const bool hsel = (q >> 1) != 0;               // which pixel of the (x0, x0+1) pair this lane loads
+  const int cLane = (q & 1) * 8 + (q >> 1) * 4;  // first of the 4 channels (inside a group) this lane ends up owning
+  const int HW = kp.Ho * kp.Wo;
+  const int cs = kp.D * HW;                      // channel stride of vol (host checks Cout * cs < 2^31)
+  const int numOct = (kp.P + 7) >> 3;            // runs and locality groups are made of 8-pixel octets (32-byte sectors)
 
-  const long long i0 = kp.totalItems * blockIdx.x / gridDim.x;
-  const long long i1 = kp.totalItems * (blockIdx.x + 1) / gridDim.x;
-  long long curTc = -1;
-
-  for (long long item = i0; item < i1; ++item) {
-    const int b = (int)(item % kp.B);
-    const long long tc = item / kp.B;
-    const int chunk = (int)(tc % kp.numChunks);
-    const int tile = (int)(tc / kp.numChunks);
-    const int ty = tile / kp.tilesX, tx = tile % kp.tilesX;
+  for (int item = blockIdx.x; item < kp.numItems; item += gridDim.x) {
+    const int run = item / kp.numChunks, chunk = item - run * kp.numChunks;
+    const int p0 = 8 * (int)((long long)numOct * run / kp.numRuns);
+    const int p1 = min(kp.P, 8 * (int)((long long)numOct * (run + 1) / kp.numRuns));
+    const int npx = p1 - p0;
     const int d0 = chunk * kp.dch;
     const int dcount = min(kp.dch, kp.D - d0);
-    const bool newGeom = (tc != curTc) || kp.perFrameGrids;
-    curTc = tc;
+    const int npairs = npx * dcount;
+    // locality groups of about grpPx pixels: pairs are ordered (group, candidate, pixel)
+    const int ngroups = (npx + kp.grpPx - 1) / kp.grpPx;
+    const int gsz = 8 * ((((npx + 7) >> 3) + ngroups - 1) / ngroups);
 
-    // ------------------------------------------------------------------ phase 1: geometry -> tap table
-    {
-      const int h = ty * kp.tileH + p1 / kTileW, w = tx * kTileW + p1 % kTileW;
-      const bool inb = (h < kp.Ho) && (w < kp.Wo);
-      const uint32_t* mimg0 = nullptr;
-      if (AGG == MVSGI_AGG_STD) mimg0 = kp.mbits + (kp.perFrameMasks ? (long long)b * kp.mbB : 0);
-      if (newGeom) {
-        float rx = 0.f, ry = 0.f, rz = 1.f;
-        if (kp.gridMode == MVSGI_GRID_PROJECT && inb) cv_ray(rig, h, w, rx, ry, rz);
-        for (int dd = g1; dd < dcount; dd += kLanesPerPixel) {
-          const int d = d0 + dd;
-          uint32_t vbit = 0;
-#pragma unroll
-          for (int cam = 0; cam < CAM; ++cam) {
-            float gx = 2.0f, gy = 2.0f;  // far outside: all-zero taps
-            bool gvalid = false;
-            if (inb) {
-              if (kp.gridMode == MVSGI_GRID_PROJECT) {
-                float x, y, z;
-                to_camera(rig.cams[cam], rx, ry, rz, rig.dist[d], x, y, z);
-                gvalid = project(rig.cams[cam], x, y, z, gx, gy);
-              } else {
-                const long long go = (long long)b * kp.gsB + cam * kp.gsCam + d * kp.gsD + h * kp.gsY + w * kp.gsX;
-                const float2 g = __ldg(reinterpret_cast<const float2*>(kp.grids + go));
-                gx = g.x;
-                gy = g.y;
-                if (AGG == MVSGI_AGG_STD)
-                  gvalid = __ldg(kp.gmask + (long long)b * kp.gmB + cam * kp.gmCam + d * kp.gmD + h * kp.gmY +
-                                 w * kp.gmX) != 0;
-              }
-            }
-            const int e = (dd * CAM + cam) * TP + p1;
-            const TapEntry te = make_tap_entry(gx, gy, kp.Hf, kp.Wf, kp.fsY, kp.fsX);
-            tOff[e] = te.off;
-            tW[e] = te.wa;
-            tW[nEnt + e] = te.wb;
-            tW[2 * nEnt + e] = te.wc;
-            tW[3 * nEnt + e] = te.wd;
-            if (AGG == MVSGI_AGG_STD) {
-              const uint32_t info = gvalid ? make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch) : kMaskNone;
-              if (kp.perFrameMasks) tM[e] = info;
-              else if (mask_lookup(mimg0 + cam * kp.mbCam, info, kp.mPitch)) vbit |= 1u << cam;
-            }
-          }
-          if (AGG == MVSGI_AGG_STD && !kp.perFrameMasks) vb[dd * TP + p1] = (unsigned char)vbit;
-        }
-      }
-      if (AGG == MVSGI_AGG_STD && kp.perFrameMasks) {
-        // tM[(dd, cam, p1)] was written by this same thread above (identical dd striding): no barrier needed
-        for (int dd = g1; dd < dcount; dd += kLanesPerPixel) {
-          uint32_t vbit = 0;
-#pragma unroll
-          for (int cam = 0; cam < CAM; ++cam)
-            if (mask_lookup(mimg0 + cam * kp.mbCam, tM[(dd * CAM + cam) * TP + p1], kp.mPitch)) vbit |= 1u << cam;
-          vb[dd * TP + p1] = (unsigned char)vbit;
-        }
+    if (kp.gridMode == MVSGI_GRID_PROJECT) {
+      for (int p = tid; p < npx; p += kSweepThreads) {
+        const int pix = p0 + p;
+        float rx, ry, rz;
+        cv_ray(rig, pix / kp.Wo, pix % kp.Wo, rx, ry, rz);
+        rays[3 * p] = rx;
+        rays[3 * p + 1] = ry;
+        rays[3 * p + 2] = rz;
       }
     }
     __syncthreads();
 
-    // ------------------------------------------------------------------ phase 2: gather + aggregate + store
-    {
-      const int h = ty * kp.tileH + p2 / kTileW, w = tx * kTileW + p2 % kTileW;
-      const bool inb = (p2 < TP) && (h < kp.Ho) && (w < kp.Wo);
-      const long long planeHW = (long long)kp.Ho * kp.Wo;
-      const float* fb = kp.feat + (long long)b * kp.fsB;
-      for (int cg = 0; cg < kp.C; cg += 16) {
-        const int c0 = cg + q * 4;
-        const bool cact = inb && (c0 < kp.C);
-        const float* fq = fb + c0;
-        for (int dd = 0; dd < dcount; ++dd) {
-          const int d = d0 + dd;
+    // ---------------------------------------------------------------- build: geometry -> tap table
+    auto build = [&](int b) {
+      for (int e = tid; e < CAM * npairs; e += kSweepThreads) {
+        const int cam = e / npairs, j = e - cam * npairs;
+        const int gi = j / (gsz * dcount);
+        const int local = j - gi * gsz * dcount;
+        const int gcount = min(gsz, npx - gi * gsz);
+        const int dd = local / gcount;
+        const int p = gi * gsz + (local - dd * gcount);
+        const int d = d0 + dd;
+        const int pix = p0 + p;
+        const int h = pix / kp.Wo, w = pix - h * kp.Wo;
+        float gx, gy;
+        bool gvalid = true;
+        if (kp.gridMode == MVSGI_GRID_PROJECT) {
+          float x, y, z;
+          to_camera(rig.cams[cam], rays[3 * p], rays[3 * p + 1], rays[3 * p + 2], rig.dist[d], x, y, z);
+          gvalid = project(rig.cams[cam], x, y, z, gx, gy);
+        } else {
+          const long long go = (long long)b * kp.gsB + cam * kp.gsCam + d * kp.gsD + h * kp.gsY + w * kp.gsX;
+          const float2 g = __ldg(reinterpret_cast<const float2*>(kp.grids + go));
+          gx = g.x;
+          gy = g.y;
+          if (AGG == MVSGI_AGG_STD)
+            gvalid = __ldg(kp.gmask + (long long)b * kp.gmB + cam * kp.gmCam + d * kp.gmD + h * kp.gmY + w * kp.gmX) != 0;
+        }
+        int off;
+        float lx, ly;
+        make_entry(kp, gx, gy, off, lx, ly);
+        uint32_t* rec = tab + (size_t)j * ES;
+        rec[2 + 3 * cam] = (uint32_t)(off + cam * kp.fsCam);
+        rec[3 + 3 * cam] = __float_as_uint(lx);
+        rec[4 + 3 * cam] = __float_as_uint(ly);
+        if (AGG == MVSGI_AGG_STD)
+          tMi[cam * MP + j] = gvalid ? make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch) : kMaskNone;
+        if (cam == 0) {
+          rec[0] = (uint32_t)(d * HW + pix);
+          if (AGG == MVSGI_AGG_CONCAT) rec[1] = (1u << CAM) - 1u;
+        }
+      }
+    };
+    // Validity bits of every pair for frame b: consecutive threads = consecutive pixels of one camera and candidate,
+    // so the four mask-word loads of a warp fall into one or two sectors.  spherical_sweep_avg.py:92-102
+    auto lookup_masks = [&](int b) {
+      const uint32_t* mb = kp.mbits + (kp.perFrameMasks ? (long long)b * kp.mbB : 0);
+      for (int j = tid; j < npairs; j += kSweepThreads) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int cam = 0; cam < CAM; ++cam)
+          if (mask_lookup(mb + cam * kp.mbCam, tMi[cam * MP + j], kp.mPitch)) v |= 1u << cam;
+        tab[(size_t)j * ES + 1] = v;
+      }
+    };
+    if (!kp.perFrameGrids) {
+      build(0);
+      __syncthreads();
+      if (AGG == MVSGI_AGG_STD && !kp.perFrameMasks) {
+        lookup_masks(0);
+        __syncthreads();
+      }
+    }
+
+    // ---------------------------------------------------------------- sweep: frames outer
+    for (int b = 0; b < kp.B; ++b) {
+      if (kp.perFrameGrids) {
+        __syncthreads();
+        build(b);
+        __syncthreads();
+      }
+      if (AGG == MVSGI_AGG_STD && (kp.perFrameMasks || kp.perFrameGrids)) {
+        __syncthreads();  // the previous frame's readers of the validity bits are done
+        lookup_masks(b);
+        __syncthreads();
+      }
+      const float* fb = kp.feat + (long long)b * kp.fsB + q * 8;
+      float* vb = kp.vol + (long long)b * kp.Cout * cs;
+
+      const uint32_t* rec0 = tab + (size_t)(warp * 8 + (lane >> 2)) * ES;
+      for (int j0 = warp * 8; j0 < npairs; j0 += nwarps * 8, rec0 += nwarps * 8 * ES) {  // warp-uniform trip count
+        const bool act = j0 + (lane >> 2) < npairs;
+        const uint32_t* rec = act ? rec0 : tab;
+        const int po = (int)rec[0];
+        const uint32_t v = rec[1];
+        const int n = __popc(v);
+        const bool need = act && (AGG == MVSGI_AGG_CONCAT || n > 1);  // spherical_sweep_avg.py:106-111
+
+        for (int cg = 0; cg < kp.CG; ++cg) {
+          float f[CAM][4];
+          const float* fcg = fb + cg * kp.fsCg;
+#pragma unroll
+          for (int cam = 0; cam < CAM; ++cam) {
+            const bool ld = need && ((v >> cam) & 1u);
+            if (__any_sync(0xFFFFFFFFu, ld)) {
+              // lanes with nothing to sample read the all-zero patch with zero weights: no divergence, no predication
+              const int off = ld ? (int)rec[2 + 3 * cam] : kp.zeroOff;
+              const float lx = __uint_as_float(rec[3 + 3 * cam]), ly = __uint_as_float(rec[4 + 3 * cam]);
+              float wx = hsel ? lx : 1.0f - lx;
+              if (!ld) wx = 0.0f;
+              const float w1 = wx * ly, w0 = fmaf(-wx, ly, wx);
+              const float* t = fcg + off;
+              const F8 r0 = ldg256(t);
+              const F8 r1 = ldg256(t + kp.fsY);
+              // backports.py:52-55,86: this lane's pixel column of the sample, 8 channels
+              float u[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) u[i] = fmaf(w1, r1.v[i], w0 * r0.v[i]);
+              // lanes (q, q^2) hold columns x0 / x0+1 of the same 8 channels: keep 4 channels, trade the other 4
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float mine = hsel ? u[4 + i] : u[i];
+                const float send = hsel ? u[i] : u[4 + i];
+                f[cam][i] = mine + __shfl_xor_sync(0xFFFFFFFFu, send, 2);
+              }
+            } else {
+              f[cam][0] = f[cam][1] = f[cam][2] = f[cam][3] = 0.0f;
+            }
+          }
+
+          const int c0 = cg * kCG + cLane;
+          const int nst = act ? kp.C - c0 : 0;  // channels this lane stores (staged channels >= C are padding)
           if (AGG == MVSGI_AGG_STD) {
-            const uint32_t v = cact ? vb[dd * TP + p2] : 0u;
-            const int n = __popc(v);
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n > 1) {  // spherical_sweep_avg.py:106-111
-              float4 f[CAM];
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            if (need) {
+              const float inv = n == 2 ? 0.5f : (n == 3 ? (1.0f / 3.0f) : 0.25f);
 #pragma unroll
-              for (int cam = 0; cam < CAM; ++cam) {
-                f[cam] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((v >> cam) & 1u) {
-                  const int e = (dd * CAM + cam) * TP + p2;
-                  const float* t = fq + cam * kp.fsCam + tOff[e];
-                  f[cam] = bilerp(ldg4(t), ldg4(t + kp.fsY), ldg4(t + kp.fsX), ldg4(t + kp.fsY + kp.fsX), tW[e],
-                                  tW[nEnt + e], tW[2 * nEnt + e], tW[3 * nEnt + e]);
+              for (int i = 0; i < 4; ++i) {
+                float s = f[0][i];
+#pragma unroll
+                for (int cam = 1; cam < CAM; ++cam) s += f[cam][i];
+                const float avg = s * inv;  // :114
+                float acc = 0.f;
+#pragma unroll
+                for (int cam = 0; cam < CAM; ++cam) {
+                  // :119-122 masked-out cameras contribute (avg-avg)^2 = 0
+                  const float dlt = ((v >> cam) & 1u) ? f[cam][i] - avg : 0.0f;
+                  acc = fmaf(dlt, dlt, acc);
                 }
+                o[i] = acc * inv;
               }
-              const float inv = 1.0f / (float)n;
-              float4 s = f[0];
-#pragma unroll
-              for (int cam = 1; cam < CAM; ++cam) {
-                s.x += f[cam].x; s.y += f[cam].y; s.z += f[cam].z; s.w += f[cam].w;
-              }
-              const float4 avg = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);  // :114
-#pragma unroll
-              for (int cam = 0; cam < CAM; ++cam) {
-                if ((v >> cam) & 1u) {  // :119-122 masked-out cameras contribute (avg-avg)^2 = 0
-                  const float dx = f[cam].x - avg.x, dy = f[cam].y - avg.y, dz = f[cam].z - avg.z,
-                              dw = f[cam].w - avg.w;
-                  o.x = fmaf(dx, dx, o.x); o.y = fmaf(dy, dy, o.y); o.z = fmaf(dz, dz, o.z); o.w = fmaf(dw, dw, o.w);
-                }
-              }
-              o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
             }
-            if (cact) {
-              float* dst = kp.vol + (((long long)b * kp.Cout + c0) * kp.D + d) * planeHW + (long long)h * kp.Wo + w;
-              const long long cs = (long long)kp.D * planeHW;
-              __stcs(dst, o.x);
-              __stcs(dst + cs, o.y);
-              __stcs(dst + 2 * cs, o.z);
-              __stcs(dst + 3 * cs, o.w);
-              if (kp.validOut != nullptr && c0 == 0)
-                kp.validOut[((long long)b * kp.D + d) * planeHW + (long long)h * kp.Wo + w] = (n > 1) ? 1 : 0;
-            }
+            float* dst = vb + (c0 * cs + po);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < nst) __stcs(dst + i * cs, o[i]);
+            if (kp.validOut != nullptr && act && cg == 0 && q == 0)
+              kp.validOut[(long long)b * cs + po] = (n > 1) ? 1 : 0;
           } else {  // concat: spherical_sweep.py:52-67, out channel = cam*C + c, masks ignored
-            if (cact) {
 #pragma unroll
-              for (int cam = 0; cam < CAM; ++cam) {
-                const int e = (dd * CAM + cam) * TP + p2;
-                const float* t = fq + cam * kp.fsCam + tOff[e];
-                const float4 o = bilerp(ldg4(t), ldg4(t + kp.fsY), ldg4(t + kp.fsX), ldg4(t + kp.fsY + kp.fsX),
-                                        tW[e], tW[nEnt + e], tW[2 * nEnt + e], tW[3 * nEnt + e]);
-                float* dst = kp.vol + (((long long)b * kp.Cout + cam * kp.C + c0) * kp.D + d) * planeHW +
-                             (long long)h * kp.Wo + w;
-                const long long cs = (long long)kp.D * planeHW;
-                __stcs(dst, o.x);
-                __stcs(dst + cs, o.y);
-                __stcs(dst + 2 * cs, o.z);
-                __stcs(dst + 3 * cs, o.w);
-              }
+            for (int cam = 0; cam < CAM; ++cam) {
+              float* dst = vb + ((cam * kp.C + c0) * cs + po);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < nst) __stcs(dst + i * cs, f[cam][i]);
             }
           }
         }
       }
     }
-    __syncthreads();  // the next item's phase 1 overwrites the table
+    __syncthreads();  // the next item's build overwrites the table
   }
 }
 
-// ---- grid dump (mvsgi_project_only_f32): exactly the (gx, gy, valid) phase 1 computes ---------------------------
+// ---- grid dump (mvsgi_project_only_f32): exactly the (gx, gy, valid) the build step computes -----------------------
 __global__ void project_only_kernel(const __grid_constant__ MvsgiRig rig, float* __restrict__ grids,
                                     uint8_t* __restrict__ gmask) {
   const int Ho = rig.cv_height, Wo = rig.cv_width;
@@ -333,60 +354,6 @@ __global__ void project_only_kernel(const __grid_constant__ MvsgiRig rig, float*
       grids[o * 2 + 1] = gy;
       gmask[o] = valid ? 1 : 0;
     }
-}
-
-// ---- staging kernels ---------------------------------------------------------------------------------------------
-// feats [N, C, H, W] (arbitrary element strides) -> channels-last [N, H, W, C] fp32.  32 pixels x C channels per block
-// row, transposed through shared memory so both the read (along W) and the write (along C) are coalesced.
-__global__ void __launch_bounds__(256)
-nhwc_stage_kernel(const float* __restrict__ src, long long sN0, int n1, long long sN1, long long sC, long long sH,
-                  long long sW, int C, int H, int W, float* __restrict__ dst) {
-  extern __shared__ float tile[];  // [C][33]
-  const int x0 = blockIdx.x * 32, y = blockIdx.y, n = blockIdx.z;
-  const float* s = src + (long long)(n / n1) * sN0 + (long long)(n % n1) * sN1 + (long long)y * sH;
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  for (int c = wrp; c < C; c += 8) {
-    const int x = x0 + lane;
-    tile[c * 33 + lane] = (x < W) ? __ldg(s + c * sC + x * sW) : 0.0f;
-  }
-  __syncthreads();
-  const int c4n = C >> 2;  // float4 groups per pixel
-  float* d = dst + (((long long)n * H + y) * W + x0) * C;
-  for (int i = threadIdx.x; i < 32 * c4n; i += 256) {
-    const int x = i / c4n, c4 = i % c4n;
-    if (x0 + x < W) {
-      float4 v;
-      v.x = tile[(c4 * 4 + 0) * 33 + x];
-      v.y = tile[(c4 * 4 + 1) * 33 + x];
-      v.z = tile[(c4 * 4 + 2) * 33 + x];
-      v.w = tile[(c4 * 4 + 3) * 33 + x];
-      *reinterpret_cast<float4*>(d + (long long)x * C + c4 * 4) = v;
-    }
-  }
-}
-
-// masks -> padded bit images: word j of padded row Y holds bits X = 32j..32j+31, bit set iff mask(y=Y-1, x=X-1) > 0.
-template <typename T>
-__global__ void __launch_bounds__(256)
-pack_masks_kernel(const T* __restrict__ src, int n1, long long sN0, long long sN1, long long sH, long long sW, int Hm,
-                  int Wm, int pitch, uint32_t* __restrict__ bits, int* __restrict__ flags) {
-  const int n = blockIdx.z, Y = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int word = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (word >= pitch) return;
-  const int X = word * 32 + lane, x = X - 1, y = Y - 1;
-  bool set = false, bad = false;
-  if (x >= 0 && x < Wm && y >= 0 && y < Hm) {
-    const float v = (float)src[(long long)(n / n1) * sN0 + (long long)(n % n1) * sN1 + (long long)y * sH + x * sW];
-    set = v > 0.0f;
-    bad = !(v >= 0.0f);  // negative or NaN
-  }
-  const uint32_t w = __ballot_sync(0xFFFFFFFFu, set);
-  const uint32_t anybad = __ballot_sync(0xFFFFFFFFu, bad);
-  if (lane == 0) {
-    bits[((long long)n * (Hm + 2) + Y) * pitch + word] = w;
-    if (anybad && flags != nullptr) atomicOr(flags, 1);
-  }
 }
 
 }  // namespace mvsgi
