@@ -28,7 +28,7 @@ struct SweepPlan {
   int mask_pitch, mask_words;
   int cg;                 // 16-channel groups of the staged features
   int64_t feats_bytes, mask_bytes, flag_bytes, total_bytes;
-  int dch, num_chunks, num_runs, run_len, num_items, max_pairs, grid, group_px;
+  int dch, num_chunks, num_runs, run_len, num_items, max_pairs, grid, group_px, interleave;
   size_t smem_bytes;
   int cout;
 };
@@ -120,15 +120,16 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   p->num_items = p->num_runs * p->num_chunks;
   p->max_pairs = p->run_len * dch;
   p->grid = p->num_items < grid_target ? p->num_items : grid_target;
-  p->group_px = env_int("MVSGI_GROUP_PX", 32);
+  p->interleave = env_int("MVSGI_INTERLEAVE", 1) ? 1 : 0;
+  p->group_px = env_int("MVSGI_GROUP_PX", p->interleave ? 8 : 32);
   if (p->group_px < 1) p->group_px = 1;
   p->smem_bytes = align_up((int64_t)p->max_pairs * per_pair + (int64_t)p->run_len * 12 + 16, 16);
   return MVSGI_OK;
 }
 
-template <int CAM, int AGG>
+template <int CAM, int AGG, bool FULLC, bool VALID>
 cudaError_t launch_sweep(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
-  auto kern = mvsgi::sweep_kernel<CAM, AGG>;
+  auto kern = mvsgi::sweep_kernel<CAM, AGG, FULLC, VALID>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, mvsgi::kSweepThreads, smem, st>>>(kp, rig);
@@ -136,14 +137,25 @@ cudaError_t launch_sweep(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid
   return cudaGetLastError();
 }
 
+template <int CAM, int AGG>
+cudaError_t dispatch_flags(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
+  const bool fullc = kp.C % mvsgi::kCG == 0;
+  const bool valid = kp.validOut != nullptr;
+  if (AGG == MVSGI_AGG_STD && valid)
+    return fullc ? launch_sweep<CAM, AGG, true, true>(kp, rig, grid, smem, st)
+                 : launch_sweep<CAM, AGG, false, true>(kp, rig, grid, smem, st);
+  return fullc ? launch_sweep<CAM, AGG, true, false>(kp, rig, grid, smem, st)
+               : launch_sweep<CAM, AGG, false, false>(kp, rig, grid, smem, st);
+}
+
 template <int AGG>
 cudaError_t dispatch_cams(int cams, const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
                           cudaStream_t st) {
   switch (cams) {
-    case 1: return launch_sweep<1, AGG>(kp, rig, grid, smem, st);
-    case 2: return launch_sweep<2, AGG>(kp, rig, grid, smem, st);
-    case 3: return launch_sweep<3, AGG>(kp, rig, grid, smem, st);
-    default: return launch_sweep<4, AGG>(kp, rig, grid, smem, st);
+    case 1: return dispatch_flags<1, AGG>(kp, rig, grid, smem, st);
+    case 2: return dispatch_flags<2, AGG>(kp, rig, grid, smem, st);
+    case 3: return dispatch_flags<3, AGG>(kp, rig, grid, smem, st);
+    default: return dispatch_flags<4, AGG>(kp, rig, grid, smem, st);
   }
 }
 
@@ -259,7 +271,7 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
   kp.B = a->batch; kp.C = a->feat_chs; kp.D = a->num_cands; kp.Cout = p.cout; kp.CG = p.cg;
   kp.Ho = a->out_h; kp.Wo = a->out_w; kp.Hf = a->feat_h; kp.Wf = a->feat_w; kp.Hm = a->mask_h; kp.Wm = a->mask_w;
   kp.P = a->out_h * a->out_w; kp.numRuns = p.num_runs; kp.runLen = p.run_len; kp.dch = p.dch;
-  kp.numChunks = p.num_chunks; kp.numItems = p.num_items; kp.maxPairs = p.max_pairs; kp.grpPx = p.group_px;
+  kp.numChunks = p.num_chunks; kp.numItems = p.num_items; kp.maxPairs = p.max_pairs; kp.grpPx = p.group_px; kp.interleave = p.interleave;
   kp.feat = ws_feats;
   kp.fsY = Wp * mvsgi::kCG;
   kp.fsCg = Hp1 * kp.fsY;
