@@ -318,7 +318,7 @@ def run_b200(args, w):
     mask_bits_bytes = 0
     if w.aggregate == "std":
         n_img = (B if args.masks == "per_frame" else 1) * w.num_cams
-        pitch = (w.mask_hw[1] + 2 + 31) // 32 + 1
+        pitch = (w.mask_hw[1] + 31) // 32 + 2
         mask_bits_bytes = n_img * (w.mask_hw[0] + 2) * pitch * 4
     alg_bytes = B * (w.vol_bytes() + w.feats_bytes()) + mask_bits_bytes
     achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9

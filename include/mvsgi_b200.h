@@ -169,7 +169,8 @@ int mvsgi_project_only_f32(const MvsgiProjectArgs* args, void* cuda_stream);
 
 /* ---- mask packing -------------------------------------------------------- */
 /* Packs masks (>0 -> 1) into the padded bit layout the sweep samples:
- * per (n) image: (Hm+2) rows x pitch_words uint32, bit (x+1) of row (y+1).
+ * per (n) image: (Hm+2) rows x pitch_words uint32; pixel (y, x) is bit (x & 31) of word 1 + (x >> 5) of row y + 1
+ * (row 0, row Hm+1, word 0 and the words after the data are zero guards).
  * flags_out[0] gets bit0 set if any mask value is negative or NaN (then the
  * "bilinear(mask) > 0" test of spherical_sweep_avg.py:92-96 is not equivalent
  * to the packed test and the caller should reject the input). */

@@ -33,7 +33,7 @@ struct SweepPlan {
   int cout;
 };
 
-int mask_pitch_words(int mask_w) { return (mask_w + 2 + 31) / 32 + 1; }
+int mask_pitch_words(int mask_w) { return (mask_w + 31) / 32 + 2; }  // zero guard word + data words + zero guard
 
 int device_sms() {
   int dev = 0, sms = 148;
@@ -162,16 +162,39 @@ cudaError_t dispatch_cams(int cams, const mvsgi::SweepKP& kp, const MvsgiRig& ri
 cudaError_t launch_pack(const void* masks, int dtype, int n0, int64_t s0, int n1, int64_t s1, int64_t sh, int64_t sw,
                         int Hm, int Wm, uint32_t* bits, int* flags, cudaStream_t st) {
   const int pitch = mask_pitch_words(Wm);
-  const int words = (Hm + 2) * pitch;
-  dim3 grid((words + 63) / 64, n0 * n1);
-  if (dtype == MVSGI_MASK_F32)
-    mvsgi::pack_masks_kernel<float><<<grid, 256, 0, st>>>((const float*)masks, n1, s0, s1, sh, sw, Hm, Wm, pitch, words,
-                                                          bits, flags);
-  else
-    mvsgi::pack_masks_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)masks, n1, s0, s1, sh, sw, Hm, Wm, pitch,
-                                                            words, bits, flags);
+  if (Hm + 2 > 65535 * 32767 || n0 * (int64_t)n1 > 65535) return cudaErrorInvalidValue;
+  dim3 grid(Hm + 2, n0 * n1);
+  const int esz = dtype == MVSGI_MASK_F32 ? 4 : 1;
+  // 4 pixels per lane in one load: rows contiguous and every row start aligned to 4 elements
+  const bool vec = sw == 1 && Wm % 4 == 0 && sh % 4 == 0 && s0 % 4 == 0 && s1 % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(masks) % (4 * esz)) == 0;
+  if (dtype == MVSGI_MASK_F32) {
+    const float* m = (const float*)masks;
+    if (vec) mvsgi::pack_masks_kernel<float, true><<<grid, 256, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
+    else mvsgi::pack_masks_kernel<float, false><<<grid, 256, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
+  } else {
+    const uint8_t* m = (const uint8_t*)masks;
+    if (vec) mvsgi::pack_masks_kernel<uint8_t, true><<<grid, 256, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
+    else mvsgi::pack_masks_kernel<uint8_t, false><<<grid, 256, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
+  }
   g_launches++;
   return cudaGetLastError();
+}
+
+template <int DREG, bool FULL>
+void launch_x2_flags(const mvsgi::SoftKP& kp, dim3 grid, cudaStream_t st) {
+  const bool nc = kp.normCosts != nullptr, am = kp.argmax != nullptr;
+  if (nc && am) mvsgi::softargmin_x2_kernel<DREG, FULL, true, true><<<grid, 128, 0, st>>>(kp);
+  else if (nc) mvsgi::softargmin_x2_kernel<DREG, FULL, true, false><<<grid, 128, 0, st>>>(kp);
+  else if (am) mvsgi::softargmin_x2_kernel<DREG, FULL, false, true><<<grid, 128, 0, st>>>(kp);
+  else mvsgi::softargmin_x2_kernel<DREG, FULL, false, false><<<grid, 128, 0, st>>>(kp);
+}
+
+void launch_softargmin_x2(const mvsgi::SoftKP& kp, dim3 grid, cudaStream_t st) {
+  if (kp.D == 16) launch_x2_flags<16, true>(kp, grid, st);
+  else if (kp.D == 8) launch_x2_flags<8, true>(kp, grid, st);
+  else if (kp.D < 8) launch_x2_flags<8, false>(kp, grid, st);
+  else launch_x2_flags<16, false>(kp, grid, st);
 }
 
 }  // namespace
@@ -336,17 +359,25 @@ int mvsgi_softargmin_f32(const MvsgiSoftArgminArgs* a, void* stream) {
   kp.costs = a->costs;
   kp.sB = a->costs_stride[0]; kp.sD = a->costs_stride[1]; kp.sY = a->costs_stride[2]; kp.sX = a->costs_stride[3];
   kp.idx = a->inv_dist_idx; kp.invDist = a->inv_dist; kp.normCosts = a->norm_costs; kp.argmax = a->argmax;
-  int split = a->num_cands <= 16 ? 1 : (a->num_cands <= 32 ? 2 : 4);
-  const int forced = env_int("MVSGI_SOFTARGMIN_DSPLIT", 0);
-  if (forced == 1 || forced == 2 || forced == 4) {
-    if ((a->num_cands + forced - 1) / forced <= 16) split = forced;
-  }
-  const int ppb = 4 * (32 / split);  // output pixels per 128-thread block
-  dim3 grid((a->out_w + ppb - 1) / ppb, a->out_h, a->batch);
   cudaStream_t st = (cudaStream_t)stream;
-  if (split == 1) mvsgi::softargmin_kernel<1><<<grid, 128, 0, st>>>(kp);
-  else if (split == 2) mvsgi::softargmin_kernel<2><<<grid, 128, 0, st>>>(kp);
-  else mvsgi::softargmin_kernel<4><<<grid, 128, 0, st>>>(kp);
+  const bool x2 = kp.interp && a->out_h == 2 * a->in_h && a->out_w == 2 * a->in_w && a->src_scale_h == 0.5f &&
+                  a->src_scale_w == 0.5f && a->num_cands <= 16 && a->in_h < 65535 && (int64_t)a->out_h * a->out_w < (1ll << 31) &&
+                  llabs(a->costs_stride[1]) * a->num_cands < (1ll << 31) && !env_int("MVSGI_SOFTARGMIN_GENERIC", 0);
+  if (x2) {  // configs/base_model.yaml:28-34 (interp_scale_factor 2, pre_interp): one thread per 2x2 output block
+    dim3 grid((a->in_w + 1 + 127) / 128, a->in_h + 1, a->batch);
+    launch_softargmin_x2(kp, grid, st);
+  } else {
+    int split = a->num_cands <= 16 ? 1 : (a->num_cands <= 32 ? 2 : 4);
+    const int forced = env_int("MVSGI_SOFTARGMIN_DSPLIT", 0);
+    if (forced == 1 || forced == 2 || forced == 4) {
+      if ((a->num_cands + forced - 1) / forced <= 16) split = forced;
+    }
+    const int ppb = 4 * (32 / split);  // output pixels per 128-thread block
+    dim3 grid((a->out_w + ppb - 1) / ppb, a->out_h, a->batch);
+    if (split == 1) mvsgi::softargmin_kernel<1><<<grid, 128, 0, st>>>(kp);
+    else if (split == 2) mvsgi::softargmin_kernel<2><<<grid, 128, 0, st>>>(kp);
+    else mvsgi::softargmin_kernel<4><<<grid, 128, 0, st>>>(kp);
+  }
   g_launches++;
   return (int)cudaGetLastError();
 }

@@ -121,4 +121,97 @@ __global__ void __launch_bounds__(128) softargmin_kernel(const SoftKP kp) {
   }
 }
 
+// ---- scale-factor-2 fast path ----------------------------------------------------------------------------------------
+// With F.interpolate(scale_factor=2, align_corners=False) the 2x2 block of output pixels (2k+1, 2k+2) x (2m+1, 2m+2)
+// reads exactly the 2x2 input neighbourhood rows (k, k+1) x columns (m, m+1) (clamped at the border; k, m = -1 is the
+// first output row / column on its own).  One thread owns such a block: 4 coalesced loads per candidate feed 4 output
+// pixels (16 per pixel in the generic kernel), all D candidates of the 4 pixels stay in registers, and the softmax uses
+// one reciprocal per pixel.  The interpolated values are computed with the same src_index() weights and the same fma
+// placement as the generic kernel, so the arg-max candidate stays bit-exact against PyTorch's CPU upsample.
+template <int DREG, bool FULL, bool NC, bool AM>  // FULL: D == DREG; NC / AM: norm_costs / argmax requested
+__global__ void __launch_bounds__(128) softargmin_x2_kernel(const SoftKP kp) {
+  const int m = blockIdx.x * 128 + threadIdx.x - 1;  // -1 .. Win-1
+  const int k = blockIdx.y - 1;                      // -1 .. Hin-1
+  const int b = blockIdx.z;
+  if (m >= kp.Win) return;
+  const int D = FULL ? DREG : kp.D;
+  const int ra = max(k, 0), rb = min(ra + 1, kp.Hin - 1);
+  const int ca = max(m, 0), cb = min(ca + 1, kp.Win - 1);
+  const float* p00 = kp.costs + (long long)b * kp.sB + ra * kp.sY + ca * kp.sX;
+  const int dx = (int)((cb - ca) * kp.sX), dy = (int)((rb - ra) * kp.sY);  // 0 at the clamped border
+  const int sD = (int)kp.sD;  // host checks that one frame of costs spans < 2^31 elements
+
+  // weights of the (up to) two output rows / columns of this block
+  float ly0[2], ly1[2], lx0[2], lx1[2];
+  bool rowok[2], colok[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int oy = 2 * k + 1 + r, ox = 2 * m + 1 + r;
+    int i0, i1;
+    rowok[r] = oy >= 0 && oy < kp.Hout;
+    colok[r] = ox >= 0 && ox < kp.Wout;
+    src_index(max(oy, 0), kp.scaleH, kp.Hin, i0, i1, ly0[r], ly1[r]);
+    src_index(max(ox, 0), kp.scaleW, kp.Win, i0, i1, lx0[r], lx1[r]);
+  }
+
+  float v[4][DREG];  // [row r * 2 + column c][candidate]
+  float idx[DREG];
+#pragma unroll
+  for (int d = 0; d < DREG; ++d) {
+    idx[d] = 0.f;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) v[px][d] = -CUDART_INF_F;
+    if (FULL || d < D) {
+      const float* pl = p00 + d * sD;
+      const float v00 = __ldg(pl), v01 = __ldg(pl + dx), v10 = __ldg(pl + dy), v11 = __ldg(pl + dy + dx);
+      idx[d] = __ldg(kp.idx + d);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float top = __fmaf_rn(lx0[c], v00, __fmul_rn(lx1[c], v01));
+        const float bot = __fmaf_rn(lx0[c], v10, __fmul_rn(lx1[c], v11));
+#pragma unroll
+        for (int r = 0; r < 2; ++r) v[r * 2 + c][d] = __fmaf_rn(ly0[r], top, __fmul_rn(ly1[r], bot));
+      }
+    }
+  }
+
+  const int hw = kp.Hout * kp.Wout;
+  float* nc = NC ? kp.normCosts + (long long)b * D * hw : nullptr;
+#pragma unroll
+  for (int px = 0; px < 4; ++px) {
+    const int r = px >> 1, c = px & 1;
+    if (!(rowok[r] && colok[c])) continue;
+    const int opix = (2 * k + 1 + r) * kp.Wout + (2 * m + 1 + c);
+    float mx = v[px][0];
+    int am = 0;
+#pragma unroll
+    for (int d = 1; d < DREG; ++d) {
+      if (AM) {
+        if (v[px][d] > mx) {  // strict '>' keeps the first maximum, like torch.argmax (unused slots hold -inf)
+          mx = v[px][d];
+          am = d;
+        }
+      } else {
+        mx = fmaxf(mx, v[px][d]);
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int d = 0; d < DREG; ++d) {
+      v[px][d] = __expf(v[px][d] - mx);  // exp(-inf) = 0 for unused slots
+      sum += v[px][d];
+    }
+    const float rs = 1.0f / sum;
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < DREG; ++d) {
+      const float p = v[px][d] * rs;
+      if (NC && (FULL || d < D)) __stcs(nc + (long long)d * hw + opix, p);
+      acc = __fmaf_rn(p, idx[d], acc);
+    }
+    kp.invDist[(long long)b * hw + opix] = acc;
+    if (AM) kp.argmax[(long long)b * hw + opix] = am;
+  }
+}
+
 }  // namespace mvsgi

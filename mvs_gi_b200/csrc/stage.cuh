@@ -4,8 +4,7 @@
 //                        zero-padded, channel-group-major, channels-last fp32 images [B*CAM][CG][Hf+3][Wf+2][16].
 //                        The zero frame is the F.pad of the reference sampler (dsta_mvs/model/backports/backports.py:58);
 //                        row Hf+2 is an extra all-zero row (target of far-outside samples); channels >= C are zero.
-//   pack_masks_kernel  : masks [.., Hm, Wm] (float32 0/1 or u8/bool) -> padded bit images, word j of padded row Y holds
-//                        bits X = 32j..32j+31, bit set iff mask(y = Y-1, x = X-1) > 0
+//   pack_masks_kernel  : masks [.., Hm, Wm] (float32 0/1 or u8/bool) -> zero-framed bit images, bit set iff mask > 0
 //                        (the "bilinear(mask) > 0" test of spherical_sweep_avg.py:92-96 only needs those bits).
 #pragma once
 #include <cuda_runtime.h>
@@ -69,38 +68,63 @@ stage_feats_kernel(const float* __restrict__ src, long long sN0, int n1, long lo
   }
 }
 
-// One warp packs 8 consecutive words (256 mask pixels) per step with 8 independent loads per lane in flight.
+// One block packs one padded row of one mask image: every lane reads 4 consecutive mask pixels (one 16-byte load when
+// VEC), turns them into a nibble, and 8 lanes OR their nibbles into a word with three shuffles.
+// Bit layout: padded row Y = y + 1 (rows 0 and Hm + 1 are zero); word 0 of a row is a zero guard, pixel x is bit
+// (x & 31) of word 1 + (x >> 5), and at least one zero guard word follows, so taps x0 = -1 and x0 + 1 = Wm read zeros.
 // flags[0] bit0 is set when any mask value is negative or NaN (then the packed test is not equivalent to the
 // reference's float test and the caller must reject the input).
 template <typename T>
+struct Vec4Of;
+template <>
+struct Vec4Of<float> {
+  using type = float4;
+};
+template <>
+struct Vec4Of<uint8_t> {
+  using type = uchar4;
+};
+
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
 pack_masks_kernel(const T* __restrict__ src, int n1, long long sN0, long long sN1, long long sH, long long sW, int Hm,
-                  int Wm, int pitch, int wordsPerImage, uint32_t* __restrict__ bits, int* __restrict__ flags) {
-  const int n = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);  // warp index inside the image
-  const int word0 = gw * 8;
-  if (word0 >= wordsPerImage) return;
-  const T* s = src + (long long)(n / n1) * sN0 + (long long)(n % n1) * sN1;
-  float v[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int word = word0 + k;
-    const int Y = word / pitch, wj = word - Y * pitch;
-    const int x = wj * 32 + lane - 1, y = Y - 1;
-    v[k] = 0.0f;
-    if (word < wordsPerImage && x >= 0 && x < Wm && y >= 0 && y < Hm)
-      v[k] = (float)s[(long long)y * sH + (long long)x * sW];
+                  int Wm, int pitch, uint32_t* __restrict__ bits, int* __restrict__ flags) {
+  const int n = blockIdx.y, Y = blockIdx.x, t = threadIdx.x, lane = t & 31;
+  uint32_t* row = bits + ((long long)n * (Hm + 2) + Y) * pitch;
+  const int dataWords = (Wm + 31) >> 5;
+  if (Y == 0 || Y == Hm + 1) {
+    for (int j = t; j < pitch; j += 256) row[j] = 0u;
+    return;
   }
+  if (t == 0) row[0] = 0u;
+  for (int j = 1 + dataWords + t; j < pitch; j += 256) row[j] = 0u;
+  const T* s = src + (long long)(n / n1) * sN0 + (long long)(n % n1) * sN1 + (long long)(Y - 1) * sH;
   bool bad = false;
-  uint32_t out = 0;
+  for (int xb = (t & ~31) * 4; xb < dataWords * 32; xb += 1024) {  // warp-uniform trip count (shuffles below)
+    const int x0 = xb + lane * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (VEC) {
+      if (x0 < Wm) {  // Wm % 4 == 0 on this path
+        const typename Vec4Of<T>::type q = *reinterpret_cast<const typename Vec4Of<T>::type*>(s + x0);
+        v[0] = (float)q.x; v[1] = (float)q.y; v[2] = (float)q.z; v[3] = (float)q.w;
+      }
+    } else {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    bad |= !(v[k] >= 0.0f);  // negative or NaN
-    const uint32_t w = __ballot_sync(0xFFFFFFFFu, v[k] > 0.0f);
-    if (lane == k) out = w;
+      for (int i = 0; i < 4; ++i)
+        if (x0 + i < Wm) v[i] = (float)s[(long long)(x0 + i) * sW];
+    }
+    uint32_t nib = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bad |= !(v[i] >= 0.0f);  // negative or NaN
+      nib |= (v[i] > 0.0f ? 1u : 0u) << i;
+    }
+    uint32_t w = nib << (4 * (lane & 7));
+    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
+    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
+    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
+    if ((lane & 7) == 0 && (x0 >> 5) < dataWords) row[1 + (x0 >> 5)] = w;
   }
-  if (lane < 8 && word0 + lane < wordsPerImage) bits[(long long)n * wordsPerImage + word0 + lane] = out;
   if (__any_sync(0xFFFFFFFFu, bad) && lane == 0 && flags != nullptr) atomicOr(flags, 1);
 }
 

@@ -63,7 +63,7 @@ MVSGI_DEV float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const floa
 
 // Mask test of spherical_sweep_avg.py:92-96 for 0/1 (non-negative) masks: bilinear(mask) > 0  <=>  some tap has
 // weight > 0 and a set mask bit.  Encodes the padded bit position of tap (y0, x0) and which of the other three taps
-// carry a non-zero weight.  kMaskNone (= 0: bit (0, 0) of the zero frame, no other tap) = no tap can contribute, so the
+// carry a non-zero weight.  kMaskNone (= 0: a bit of the zero frame, no other tap) = no tap can contribute, so the
 // lookup needs no branch.
 MVSGI_DEV uint32_t make_mask_info(float gx, float gy, int Hm, int Wm, int mPitch) {
   const float x = unnormalise(gx, Wm), y = unnormalise(gy, Hm);
@@ -71,8 +71,8 @@ MVSGI_DEV uint32_t make_mask_info(float gx, float gy, int Hm, int Wm, int mPitch
   const float fx0 = floorf(x), fy0 = floorf(y);
   const float hx = fsub(fadd(fx0, 1.0f), x), lx = fsub(x, fx0);
   const float hy = fsub(fadd(fy0, 1.0f), y), ly = fsub(y, fy0);
-  const int X0 = (int)fx0 + 1, Y0 = (int)fy0 + 1;  // padded coordinates
-  uint32_t info = (uint32_t)(Y0 * mPitch * 32 + X0);
+  const int x0 = (int)fx0, Y0 = (int)fy0 + 1;  // padded row; bit 32 + x of a row is pixel x (stage.cuh)
+  uint32_t info = (uint32_t)(Y0 * mPitch * 32 + 32 + x0);
   if (fmul(hx, ly) > 0.0f) info |= 1u << 28;  // wb: (x0, y1)
   if (fmul(lx, hy) > 0.0f) info |= 1u << 29;  // wc: (x1, y0)
   if (fmul(lx, ly) > 0.0f) info |= 1u << 30;  // wd: (x1, y1)
