@@ -12,8 +12,8 @@
 
 namespace mvsgi {
 
-constexpr int kStagePx = 128;     // padded pixels per block
-constexpr int kStagePitch = 130;  // smem row pitch in floats (== 2 mod 32: conflict-free both ways)
+constexpr int kStagePx = 544;     // padded pixels per block (one block covers a whole 514-pixel padded row)
+constexpr int kStagePitch = 546;  // smem row pitch in floats (== 2 mod 8: conflict-free both ways)
 
 __global__ void __launch_bounds__(256)
 stage_feats_kernel(const float* __restrict__ src, long long sN0, int n1, long long sN1, long long sC, long long sH,
@@ -27,44 +27,48 @@ stage_feats_kernel(const float* __restrict__ src, long long sN0, int n1, long lo
   const int yp = blockIdx.y;
   const int xp0 = xb * kStagePx;
   const int t = threadIdx.x;
-  float* drow = dst + (((long long)ncg * Hp1 + yp) * Wp + xp0) * 16;
+  float4* drow = reinterpret_cast<float4*>(dst + (((long long)ncg * Hp1 + yp) * Wp + xp0) * 16);
   const int npx = min(kStagePx, Wp - xp0);
 
-  const bool zero_row = (yp == 0) || (yp > Hf);
-  if (!zero_row) {
-    const float* s = src + (long long)(n / n1) * sN0 + (long long)(n % n1) * sN1 + (long long)(yp - 1) * sH;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      int c, i;
-      if (chanFastest) {  // channels-last source: 16 consecutive lanes read 16 consecutive channels
-        const int idx = t + 256 * k;
-        c = idx & 15;
-        i = idx >> 4;
-      } else {  // NCHW source: a warp reads 32 consecutive pixels of one channel
-        c = (t >> 5) + 8 * (k & 1);
-        i = (t & 31) + 32 * (k >> 1);
-      }
+  if ((yp == 0) || (yp > Hf)) {  // zero frame rows
+    for (int idx = t; idx < npx * 4; idx += 256) drow[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float* s = src + (long long)(n / n1) * sN0 + (long long)(n % n1) * sN1 + (long long)(yp - 1) * sH;
+  if (chanFastest) {  // channels-last source: 16 consecutive lanes read the 16 channels of one pixel
+#pragma unroll 4
+    for (int idx = t; idx < npx * 16; idx += 256) {
+      const int c = idx & 15, i = idx >> 4;
       const int x = xp0 + i - 1, ch = cg * 16 + c;
       float v = 0.0f;
       if (x >= 0 && x < Wf && ch < C) v = __ldg(s + (long long)ch * sC + (long long)x * sW);
       tile[c * kStagePitch + i] = v;
     }
+  } else {  // NCHW source: a warp reads 32 consecutive pixels of one channel; all loads of a thread are independent
+    const int lane = t & 31, wrp = t >> 5;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = wrp + 8 * cc, ch = cg * 16 + c;
+      const float* sc = s + (long long)ch * sC;
+#pragma unroll
+      for (int k = 0; k < kStagePx / 32; ++k) {
+        const int i = lane + 32 * k;
+        const int x = xp0 + i - 1;
+        float v = 0.0f;
+        if (i < npx && x >= 0 && x < Wf && ch < C) v = __ldg(sc + (long long)x * sW);
+        tile[c * kStagePitch + i] = v;
+      }
+    }
   }
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int idx = t + 256 * k;  // float4 index inside the block's [px][16] output
+  for (int idx = t; idx < npx * 4; idx += 256) {  // float4 index inside the block's [px][16] output
     const int px = idx >> 2, c4 = idx & 3;
-    if (px < npx) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!zero_row) {
-        v.x = tile[(c4 * 4 + 0) * kStagePitch + px];
-        v.y = tile[(c4 * 4 + 1) * kStagePitch + px];
-        v.z = tile[(c4 * 4 + 2) * kStagePitch + px];
-        v.w = tile[(c4 * 4 + 3) * kStagePitch + px];
-      }
-      *reinterpret_cast<float4*>(drow + (long long)px * 16 + c4 * 4) = v;
-    }
+    float4 v;
+    v.x = tile[(c4 * 4 + 0) * kStagePitch + px];
+    v.y = tile[(c4 * 4 + 1) * kStagePitch + px];
+    v.z = tile[(c4 * 4 + 2) * kStagePitch + px];
+    v.w = tile[(c4 * 4 + 3) * kStagePitch + px];
+    drow[idx] = v;
   }
 }
 

@@ -24,6 +24,7 @@ constexpr int ITERS = 2000;
 // mode 3: LDG.256 dense  (1024 B contiguous)
 // mode 4: LDG.128 pair via 8 lanes per pixel (4 pixels x 128 B)  useful 512 B
 // mode 5: LDS.128 sparse from shared memory (same addresses as mode 0)
+// mode 7: LDG.256, 2 lanes per pixel (16 px x 64 B, stride 1.6 px)   useful 1024 B
 // mode 6: LDG.128 sparse, but 2 rows (half the warp row y0, other half row y1) -> 4 px x 2 rows
 template <int MODE>
 __global__ void __launch_bounds__(512) k(const float* __restrict__ buf, float* out, long long* cyc) {
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(512) k(const float* __restrict__ buf, float* o
   else if (MODE == 2) base = lane * 4;
   else if (MODE == 3) base = lane * 8;
   else if (MODE == 4) base = ((int)(1.6f * (lane >> 3))) * 16 + (lane & 7) * 4;
+  else if (MODE == 7) base = ((int)(1.6f * (lane >> 1))) * 16 + (lane & 1) * 8;
   else base = ((int)(1.6f * (quad & 3))) * 16 + q * 4 + (quad >> 2) * 514 * 16;
   const int rowspan = (MODE == 6) ? 2 : 4;
   long long t0 = clock64();
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(512) k(const float* __restrict__ buf, float* o
     for (int u = 0; u < 4; ++u) {
       int idx = (base + o + u * 16 * 29) % (WIN - rowspan * 514 * 16 > 0 ? WIN - 64 : WIN - 64);
       idx &= ~3;
-      if (MODE == 1 || MODE == 3) { idx &= ~7; F8 r = ldg256(buf + idx); acc += (r.v[0] + r.v[1]) + (r.v[2] + r.v[3]) + (r.v[4] + r.v[5]) + (r.v[6] + r.v[7]); }
+      if (MODE == 1 || MODE == 3 || MODE == 7) { idx &= ~7; F8 r = ldg256(buf + idx); acc += (r.v[0] + r.v[1]) + (r.v[2] + r.v[3]) + (r.v[4] + r.v[5]) + (r.v[6] + r.v[7]); }
       else if (MODE == 5) { float4 r = *reinterpret_cast<const float4*>(sm + idx); acc += (r.x + r.y) + (r.z + r.w); }
       else { float4 r = ldg128(buf + idx); acc += (r.x + r.y) + (r.z + r.w); }
     }
@@ -88,5 +90,6 @@ int main() {
   run<4>("LDG.128 pair, 8 lanes/px (4px x 128B)", 16, buf, out, cyc, blocks);
   run<5>("LDS.128 sparse (smem, quad=64B)", 16, buf, out, cyc, blocks);
   run<6>("LDG.128 sparse, 4px x 2 rows", 16, buf, out, cyc, blocks);
+  run<7>("LDG.256, 2 lanes/px (16px x 64B, stride 1.6px)", 32, buf, out, cyc, blocks);
   return 0;
 }
