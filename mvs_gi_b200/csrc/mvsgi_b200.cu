@@ -170,12 +170,12 @@ cudaError_t launch_pack(const void* masks, int dtype, int n0, int64_t s0, int n1
                    (reinterpret_cast<uintptr_t>(masks) % (4 * esz)) == 0;
   if (dtype == MVSGI_MASK_F32) {
     const float* m = (const float*)masks;
-    if (vec) mvsgi::pack_masks_kernel<float, true><<<grid, 256, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
-    else mvsgi::pack_masks_kernel<float, false><<<grid, 256, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
+    if (vec) mvsgi::pack_masks_kernel<float, true><<<grid, mvsgi::kPackThreads, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
+    else mvsgi::pack_masks_kernel<float, false><<<grid, mvsgi::kPackThreads, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
   } else {
     const uint8_t* m = (const uint8_t*)masks;
-    if (vec) mvsgi::pack_masks_kernel<uint8_t, true><<<grid, 256, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
-    else mvsgi::pack_masks_kernel<uint8_t, false><<<grid, 256, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
+    if (vec) mvsgi::pack_masks_kernel<uint8_t, true><<<grid, mvsgi::kPackThreads, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
+    else mvsgi::pack_masks_kernel<uint8_t, false><<<grid, mvsgi::kPackThreads, 0, st>>>(m, n1, s0, s1, sh, sw, Hm, Wm, pitch, bits, flags);
   }
   g_launches++;
   return cudaGetLastError();
@@ -362,7 +362,9 @@ int mvsgi_softargmin_f32(const MvsgiSoftArgminArgs* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool x2 = kp.interp && a->out_h == 2 * a->in_h && a->out_w == 2 * a->in_w && a->src_scale_h == 0.5f &&
                   a->src_scale_w == 0.5f && a->num_cands <= 16 && a->in_h < 65535 && (int64_t)a->out_h * a->out_w < (1ll << 31) &&
-                  llabs(a->costs_stride[1]) * a->num_cands < (1ll << 31) && !env_int("MVSGI_SOFTARGMIN_GENERIC", 0);
+                  a->costs_stride[1] >= 0 && a->costs_stride[2] >= 0 && a->costs_stride[3] >= 0 &&
+                  a->costs_stride[1] * a->num_cands + a->costs_stride[2] * a->in_h + a->costs_stride[3] * a->in_w < (1ll << 31) &&
+                  !env_int("MVSGI_SOFTARGMIN_GENERIC", 0);
   if (x2) {  // configs/base_model.yaml:28-34 (interp_scale_factor 2, pre_interp): one thread per 2x2 output block
     dim3 grid((a->in_w + 1 + 127) / 128, a->in_h + 1, a->batch);
     launch_softargmin_x2(kp, grid, st);

@@ -26,6 +26,12 @@ struct SoftKP {
   int* argmax;
 };
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void src_index(int dst, float scale, int nIn, int& i0, int& i1, float& l0, float& l1) {
   float src = __fmaf_rn(scale, (float)dst + 0.5f, -0.5f);
   src = fmaxf(src, 0.0f);
@@ -137,9 +143,11 @@ __global__ void __launch_bounds__(128) softargmin_x2_kernel(const SoftKP kp) {
   const int D = FULL ? DREG : kp.D;
   const int ra = max(k, 0), rb = min(ra + 1, kp.Hin - 1);
   const int ca = max(m, 0), cb = min(ca + 1, kp.Win - 1);
-  const float* p00 = kp.costs + (long long)b * kp.sB + ra * kp.sY + ca * kp.sX;
-  const int dx = (int)((cb - ca) * kp.sX), dy = (int)((rb - ra) * kp.sY);  // 0 at the clamped border
-  const int sD = (int)kp.sD;  // host checks that one frame of costs spans < 2^31 elements
+  // one frame of costs spans < 2^31 elements (host check): 32-bit element offsets from the frame base
+  const float* fb = kp.costs + (long long)b * kp.sB;
+  const int o00 = ra * (int)kp.sY + ca * (int)kp.sX;
+  const int dx = (cb - ca) * (int)kp.sX, dy = (rb - ra) * (int)kp.sY;  // 0 at the clamped border
+  const int sD = (int)kp.sD;
 
   // weights of the (up to) two output rows / columns of this block
   float ly0[2], ly1[2], lx0[2], lx1[2];
@@ -162,8 +170,10 @@ __global__ void __launch_bounds__(128) softargmin_x2_kernel(const SoftKP kp) {
 #pragma unroll
     for (int px = 0; px < 4; ++px) v[px][d] = -CUDART_INF_F;
     if (FULL || d < D) {
-      const float* pl = p00 + d * sD;
-      const float v00 = __ldg(pl), v01 = __ldg(pl + dx), v10 = __ldg(pl + dy), v11 = __ldg(pl + dy + dx);
+      // non-negative 32-bit element offsets (host check) -> one IMAD.WIDE.U32 per address
+      const unsigned o = (unsigned)(o00 + d * sD);
+      const float v00 = __ldg(fb + o), v01 = __ldg(fb + (o + (unsigned)dx)), v10 = __ldg(fb + (o + (unsigned)dy)),
+                  v11 = __ldg(fb + (o + (unsigned)(dy + dx)));
       idx[d] = __ldg(kp.idx + d);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -177,6 +187,7 @@ __global__ void __launch_bounds__(128) softargmin_x2_kernel(const SoftKP kp) {
 
   const int hw = kp.Hout * kp.Wout;
   float* nc = NC ? kp.normCosts + (long long)b * D * hw : nullptr;
+  constexpr float kLog2e = 1.4426950408889634f;
 #pragma unroll
   for (int px = 0; px < 4; ++px) {
     const int r = px >> 1, c = px & 1;
@@ -195,21 +206,24 @@ __global__ void __launch_bounds__(128) softargmin_x2_kernel(const SoftKP kp) {
         mx = fmaxf(mx, v[px][d]);
       }
     }
-    float sum = 0.f;
+    // softmax numerators 2^((v - max) * log2 e): one FFMA + one MUFU.EX2 each (ex2.approx.ftz, 2 ulp); the expectation
+    // is accumulated on the un-normalised numerators and scaled once (distance_regressor.py:62-78)
+    const float mlog = mx * kLog2e;
+    float sum = 0.f, acc = 0.f;
 #pragma unroll
     for (int d = 0; d < DREG; ++d) {
-      v[px][d] = __expf(v[px][d] - mx);  // exp(-inf) = 0 for unused slots
-      sum += v[px][d];
+      const float e = ex2_ftz(__fmaf_rn(v[px][d], kLog2e, -mlog));  // 2^-inf = 0 for unused slots
+      v[px][d] = e;
+      sum += e;
+      acc = __fmaf_rn(e, idx[d], acc);
     }
     const float rs = 1.0f / sum;
-    float acc = 0.f;
+    if (NC) {
 #pragma unroll
-    for (int d = 0; d < DREG; ++d) {
-      const float p = v[px][d] * rs;
-      if (NC && (FULL || d < D)) __stcs(nc + (long long)d * hw + opix, p);
-      acc = __fmaf_rn(p, idx[d], acc);
+      for (int d = 0; d < DREG; ++d)
+        if (FULL || d < D) __stcs(nc + (long long)d * hw + opix, v[px][d] * rs);
     }
-    kp.invDist[(long long)b * hw + opix] = acc;
+    kp.invDist[(long long)b * hw + opix] = acc * rs;
     if (AM) kp.argmax[(long long)b * hw + opix] = am;
   }
 }

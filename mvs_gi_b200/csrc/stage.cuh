@@ -89,45 +89,60 @@ struct Vec4Of<uint8_t> {
   using type = uchar4;
 };
 
+// masks are read exactly once: keep them out of L1 and mark them evict-first in L2
+__device__ __forceinline__ float4 ld_stream4(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ uchar4 ld_stream4(const uchar4* p) { return __ldcs(p); }
+
+constexpr int kPackThreads = 128;
+
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPackThreads)
 pack_masks_kernel(const T* __restrict__ src, int n1, long long sN0, long long sN1, long long sH, long long sW, int Hm,
                   int Wm, int pitch, uint32_t* __restrict__ bits, int* __restrict__ flags) {
   const int n = blockIdx.y, Y = blockIdx.x, t = threadIdx.x, lane = t & 31;
   uint32_t* row = bits + ((long long)n * (Hm + 2) + Y) * pitch;
   const int dataWords = (Wm + 31) >> 5;
   if (Y == 0 || Y == Hm + 1) {
-    for (int j = t; j < pitch; j += 256) row[j] = 0u;
+    for (int j = t; j < pitch; j += kPackThreads) row[j] = 0u;
     return;
   }
   if (t == 0) row[0] = 0u;
-  for (int j = 1 + dataWords + t; j < pitch; j += 256) row[j] = 0u;
+  for (int j = 1 + dataWords + t; j < pitch; j += kPackThreads) row[j] = 0u;
   const T* s = src + (long long)(n / n1) * sN0 + (long long)(n % n1) * sN1 + (long long)(Y - 1) * sH;
   bool bad = false;
-  for (int xb = (t & ~31) * 4; xb < dataWords * 32; xb += 1024) {  // warp-uniform trip count (shuffles below)
-    const int x0 = xb + lane * 4;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (VEC) {
-      if (x0 < Wm) {  // Wm % 4 == 0 on this path
-        const typename Vec4Of<T>::type q = *reinterpret_cast<const typename Vec4Of<T>::type*>(s + x0);
-        v[0] = (float)q.x; v[1] = (float)q.y; v[2] = (float)q.z; v[3] = (float)q.w;
+  constexpr int U = 4;  // row segments per thread with all loads issued before the first use (kPackThreads * 16 pixels per pass)
+  for (int xb0 = (t & ~31) * 4; xb0 < dataWords * 32; xb0 += kPackThreads * 4 * U) {  // warp-uniform trip count (shuffles below)
+    float v[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int x0 = xb0 + u * (kPackThreads * 4) + lane * 4;
+      v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+      if (VEC) {
+        if (x0 < Wm) {  // Wm % 4 == 0 on this path
+          const typename Vec4Of<T>::type q = ld_stream4(reinterpret_cast<const typename Vec4Of<T>::type*>(s + x0));
+          v[u][0] = (float)q.x; v[u][1] = (float)q.y; v[u][2] = (float)q.z; v[u][3] = (float)q.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (x0 + i < Wm) v[u][i] = (float)s[(long long)(x0 + i) * sW];
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (x0 + i < Wm) v[i] = (float)s[(long long)(x0 + i) * sW];
     }
-    uint32_t nib = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      bad |= !(v[i] >= 0.0f);  // negative or NaN
-      nib |= (v[i] > 0.0f ? 1u : 0u) << i;
+    for (int u = 0; u < U; ++u) {
+      const int x0 = xb0 + u * (kPackThreads * 4) + lane * 4;
+      uint32_t nib = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        bad |= !(v[u][i] >= 0.0f);  // negative or NaN
+        nib |= (v[u][i] > 0.0f ? 1u : 0u) << i;
+      }
+      uint32_t w = nib << (4 * (lane & 7));
+      w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
+      w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
+      w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
+      if ((lane & 7) == 0 && (x0 >> 5) < dataWords) row[1 + (x0 >> 5)] = w;
     }
-    uint32_t w = nib << (4 * (lane & 7));
-    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
-    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
-    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
-    if ((lane & 7) == 0 && (x0 >> 5) < dataWords) row[1 + (x0 >> 5)] = w;
   }
   if (__any_sync(0xFFFFFFFFu, bad) && lane == 0 && flags != nullptr) atomicOr(flags, 1);
 }
