@@ -7,8 +7,9 @@
  * interface it replaces (paths relative to the reference checkout).
  *
  * Ownership: the caller allocates every input, output and workspace buffer.
- * The library never allocates, frees or retains device memory; pointers are
- * borrowed for the duration of the enqueue.  Calibration (MvsgiRig) is read
+ * The compute entry points never allocate, free or retain device memory;
+ * pointers are borrowed for the duration of the enqueue.  (The only calls that
+ * allocate are the explicit mvsgi_p2p_* helpers at the end of this file.)  Calibration (MvsgiRig) is read
  * from HOST memory at enqueue time and passed to the kernels by value.
  *
  * Threading/streams: re-entrant, no global mutable state.  Work is enqueued on
@@ -28,9 +29,10 @@
 extern "C" {
 #endif
 
-#define MVSGI_ABI_VERSION 3
+#define MVSGI_ABI_VERSION 4
 #define MVSGI_MAX_CAMS 4
 #define MVSGI_MAX_CANDS 64
+#define MVSGI_MAX_PEERS 7 /* extra destinations of a candidate-sharded sweep (8 GPUs of one box) */
 
 /* ---- error codes ------------------------------------------------------- */
 #define MVSGI_OK 0
@@ -140,6 +142,19 @@ typedef struct MvsgiSweepArgs {
 
   void* workspace;         /* >= mvsgi_sweep_workspace_bytes(args), 256-byte aligned */
   int64_t workspace_bytes;
+
+  /* Candidate-sharded sweep (one process per GPU, BASELINE.json config 5): this call sweeps num_cands candidates
+   * that are candidates [cand_offset, cand_offset + num_cands) of a volume with vol_num_cands candidates, i.e.
+   * vol is [B, Cout, vol_num_cands, Ho, Wo].  vol_num_cands == 0 means "not sharded" (= num_cands, offset 0).
+   * Every voxel is additionally stored to the same position of each peer_vols[i] (i < num_peers): device pointers
+   * to the other GPUs' volumes mapped into this process (mvsgi_p2p_open), so the all-gather of the candidate
+   * slices happens inside the sweep, store by store over NVLink, instead of as a collective afterwards.
+   * valid_out must be NULL when num_peers > 0. */
+  int32_t cand_offset;
+  int32_t vol_num_cands;
+  int32_t num_peers;
+  int32_t reserved1;
+  float* peer_vols[MVSGI_MAX_PEERS];
 } MvsgiSweepArgs;
 
 /* Scratch the sweep needs for this problem (channels-last staging of feats when
@@ -200,6 +215,18 @@ typedef struct MvsgiSoftArgminArgs {
   int32_t* argmax;         /* [B, out_h, out_w] first-max candidate index, or NULL */
 } MvsgiSoftArgminArgs;
 int mvsgi_softargmin_f32(const MvsgiSoftArgminArgs* args, void* cuda_stream);
+
+/* ---- peer-mapped volumes for the candidate-sharded sweep ------------------- */
+/* One process per GPU.  Each rank allocates its copy of the volume with mvsgi_p2p_alloc (cudaMalloc on the current
+ * device), exports a 64-byte handle (cudaIpcGetMemHandle) that the host code sends to the other ranks
+ * (torch.distributed all_gather), and opens the other ranks' handles (cudaIpcOpenMemHandle, peer access over
+ * NVLink) to obtain the pointers it passes as MvsgiSweepArgs.peer_vols.  Returns 0 or a cudaError_t. */
+#define MVSGI_P2P_HANDLE_BYTES 64
+int mvsgi_p2p_alloc(int64_t bytes, void** ptr_out);
+int mvsgi_p2p_free(void* ptr);
+int mvsgi_p2p_export(const void* ptr, uint8_t handle_out[MVSGI_P2P_HANDLE_BYTES]);
+int mvsgi_p2p_open(const uint8_t handle[MVSGI_P2P_HANDLE_BYTES], void** ptr_out);
+int mvsgi_p2p_close(void* ptr);
 
 /* ---- misc ---------------------------------------------------------------- */
 const char* mvsgi_strerror(int code);

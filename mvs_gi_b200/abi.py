@@ -10,9 +10,11 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_CAMS = 4
 MAX_CANDS = 64
+MAX_PEERS = 7
+P2P_HANDLE_BYTES = 64
 
 CAM_EQUIRECT, CAM_DOUBLE_SPHERE, CAM_LINEAR_SPHERE = 0, 1, 2
 GRID_SUPPLIED, GRID_PROJECT = 0, 1
@@ -84,6 +86,11 @@ class MvsgiSweepArgs(C.Structure):
         ("valid_out", C.c_void_p),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
+        ("cand_offset", C.c_int32),
+        ("vol_num_cands", C.c_int32),
+        ("num_peers", C.c_int32),
+        ("reserved1", C.c_int32),
+        ("peer_vols", C.c_void_p * MAX_PEERS),
     ]
 
 
@@ -131,6 +138,11 @@ EXPORTS = {
          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
     "mvsgi_softargmin_f32": (C.c_int, [C.POINTER(MvsgiSoftArgminArgs), C.c_void_p]),
+    "mvsgi_p2p_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "mvsgi_p2p_free": (C.c_int, [C.c_void_p]),
+    "mvsgi_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mvsgi_p2p_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mvsgi_p2p_close": (C.c_int, [C.c_void_p]),
     "mvsgi_strerror": (C.c_char_p, [C.c_int]),
     "mvsgi_abi_version": (C.c_int, []),
     "mvsgi_launch_counter": (C.c_int64, []),

@@ -59,7 +59,19 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   const int64_t cg64 = (a->feat_chs + mvsgi::kCG - 1) / mvsgi::kCG;
   if ((int64_t)a->num_cams * cg64 * (a->feat_h + 3) * (a->feat_w + 2) * mvsgi::kCG >= (1ll << 31)) return MVSGI_E_SHAPE;
   const int64_t cout64 = (int64_t)a->feat_chs * (a->aggregate == MVSGI_AGG_CONCAT ? a->num_cams : 1);
-  if (cout64 * a->num_cands * a->out_h * a->out_w >= (1ll << 31)) return MVSGI_E_SHAPE;
+  // candidate-sharded call: this call's candidates are a slice of the volume's
+  if (a->vol_num_cands < 0 || a->cand_offset < 0 || a->num_peers < 0 || a->num_peers > MVSGI_MAX_PEERS) return MVSGI_E_SHAPE;
+  if (a->vol_num_cands == 0 && a->cand_offset != 0) return MVSGI_E_SHAPE;
+  const int64_t dvol64 = a->vol_num_cands > 0 ? a->vol_num_cands : a->num_cands;
+  if ((int64_t)a->cand_offset + a->num_cands > dvol64) return MVSGI_E_SHAPE;
+  if (cout64 * dvol64 * a->out_h * a->out_w >= (1ll << 31)) return MVSGI_E_SHAPE;
+  if (a->num_peers > 0) {
+    if (a->valid_out != nullptr) return MVSGI_E_UNSUPPORTED;
+    for (int i = 0; i < a->num_peers; ++i) {
+      if (a->peer_vols[i] == nullptr) return MVSGI_E_NULL;
+      if (((reinterpret_cast<uintptr_t>(a->peer_vols[i]) ^ reinterpret_cast<uintptr_t>(a->vol)) & 3) != 0) return MVSGI_E_STRIDE;
+    }
+  }
   const bool std_agg = a->aggregate == MVSGI_AGG_STD;
   if (std_agg) {
     if (a->masks == nullptr) return MVSGI_E_NULL;
@@ -127,9 +139,9 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   return MVSGI_OK;
 }
 
-template <int CAM, int AGG, bool FULLC, bool VALID>
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS = false>
 cudaError_t launch_sweep(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
-  auto kern = mvsgi::sweep_kernel<CAM, AGG, FULLC, VALID>;
+  auto kern = mvsgi::sweep_kernel<CAM, AGG, FULLC, VALID, PEERS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, mvsgi::kSweepThreads, smem, st>>>(kp, rig);
@@ -141,6 +153,9 @@ template <int CAM, int AGG>
 cudaError_t dispatch_flags(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
   const bool fullc = kp.C % mvsgi::kCG == 0;
   const bool valid = kp.validOut != nullptr;
+  if (kp.numPeers > 0)
+    return fullc ? launch_sweep<CAM, AGG, true, false, true>(kp, rig, grid, smem, st)
+                 : launch_sweep<CAM, AGG, false, false, true>(kp, rig, grid, smem, st);
   if (AGG == MVSGI_AGG_STD && valid)
     return fullc ? launch_sweep<CAM, AGG, true, true>(kp, rig, grid, smem, st)
                  : launch_sweep<CAM, AGG, false, true>(kp, rig, grid, smem, st);
@@ -322,6 +337,10 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
   }
   kp.vol = a->vol;
   kp.validOut = std_agg ? a->valid_out : nullptr;
+  kp.dOff = a->cand_offset;
+  kp.Dvol = a->vol_num_cands > 0 ? a->vol_num_cands : a->num_cands;
+  kp.numPeers = a->num_peers;
+  for (int i = 0; i < a->num_peers; ++i) kp.peerDelta[i] = (long long)((reinterpret_cast<intptr_t>(a->peer_vols[i]) - reinterpret_cast<intptr_t>(a->vol)) / 4);
 
   MvsgiRig rig;
   if (a->grid_mode == MVSGI_GRID_PROJECT) rig = *a->rig;
@@ -344,6 +363,34 @@ int mvsgi_project_only_f32(const MvsgiProjectArgs* a, void* stream) {
   g_launches++;
   return (int)cudaGetLastError();
 }
+
+// ---- peer-mapped volumes (explicit allocation helpers; see the header) -------------------------------------------
+int mvsgi_p2p_alloc(int64_t bytes, void** ptr_out) {
+  if (ptr_out == nullptr) return MVSGI_E_NULL;
+  if (bytes <= 0) return MVSGI_E_SHAPE;
+  return (int)cudaMalloc(ptr_out, (size_t)bytes);
+}
+
+int mvsgi_p2p_free(void* ptr) { return ptr ? (int)cudaFree(ptr) : MVSGI_E_NULL; }
+
+int mvsgi_p2p_export(const void* ptr, uint8_t handle_out[MVSGI_P2P_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == MVSGI_P2P_HANDLE_BYTES, "IPC handle size");
+  if (ptr == nullptr || handle_out == nullptr) return MVSGI_E_NULL;
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(ptr));
+  if (e != cudaSuccess) return (int)e;
+  memcpy(handle_out, &h, sizeof(h));
+  return MVSGI_OK;
+}
+
+int mvsgi_p2p_open(const uint8_t handle[MVSGI_P2P_HANDLE_BYTES], void** ptr_out) {
+  if (handle == nullptr || ptr_out == nullptr) return MVSGI_E_NULL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  return (int)cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+int mvsgi_p2p_close(void* ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : MVSGI_E_NULL; }
 
 int mvsgi_softargmin_f32(const MvsgiSoftArgminArgs* a, void* stream) {
   if (a == nullptr) return MVSGI_E_NULL;

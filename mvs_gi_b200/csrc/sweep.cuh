@@ -57,6 +57,10 @@ struct SweepKP {
   long long gmB, gmCam, gmD, gmY, gmX;
   float* vol;
   uint8_t* validOut;
+  // candidate-sharded sweep: the D candidates of this call are candidates [dOff, dOff + D) of a volume with Dvol
+  // candidates; every store is repeated at vol + peerDelta[i] (elements) for i < numPeers (peer-mapped volumes)
+  int dOff, Dvol, numPeers;
+  long long peerDelta[MVSGI_MAX_PEERS];
 };
 
 MVSGI_DEV float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -131,7 +135,7 @@ MVSGI_DEV void make_entry(const SweepKP& kp, float gx, float gy, int& off, float
 // The record stride is odd, so the 8 records a warp reads at a time sit in 8 different banks.
 __host__ __device__ constexpr int entry_words(int cam) { return (2 + 3 * cam) | 1; }
 
-template <int CAM, int AGG, bool FULLC, bool VALID>
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS>
 __global__ void __launch_bounds__(kSweepThreads, 2)
 sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -146,7 +150,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   constexpr int nwarps = kSweepThreads >> 5;
   const int cLane = q * 4;                       // first of the 4 channels (inside a 16-channel group) this lane owns
   const int HW = kp.Ho * kp.Wo;
-  const int cs = kp.D * HW;                      // channel stride of vol (host checks Cout * cs < 2^31)
+  const int cs = kp.Dvol * HW;                   // channel stride of vol (host checks Cout * cs < 2^31)
   const int numOct = (kp.P + 7) >> 3;            // runs and locality groups are made of 8-pixel octets (32-byte sectors)
 
   for (int item = blockIdx.x; item < kp.numItems; item += gridDim.x) {
@@ -218,7 +222,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         if (AGG == MVSGI_AGG_STD)
           tMi[cam * MP + j] = gvalid ? make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch) : kMaskNone;
         if (cam == 0) {
-          rec[0] = pixr < kp.P ? (uint32_t)(d * HW + pix) : 0xFFFFFFFFu;  // negative: nothing to store
+          rec[0] = pixr < kp.P ? (uint32_t)((d + kp.dOff) * HW + pix) : 0xFFFFFFFFu;  // negative: nothing to store
           if (AGG == MVSGI_AGG_CONCAT) rec[1] = ((1u << CAM) - 1u) * 0x0101u;
         }
       }
@@ -336,6 +340,14 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 if (i < nst) st_stream(vcg + i * (long long)csr, o[i]);
+              if (PEERS) {  // the all-gather of the candidate slices, fused: same voxel into every peer's volume
+                for (int pr = 0; pr < kp.numPeers; ++pr) {
+                  float* pv = vcg + kp.peerDelta[pr];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    if (i < nst) st_stream(pv + i * (long long)csr, o[i]);
+                }
+              }
               if (VALID && cg == 0 && q == 0) kp.validOut[(long long)b * cs + po] = (n > 1) ? 1 : 0;
             }
           } else {  // concat: spherical_sweep.py:52-67, out channel = cam*C + c, masks ignored
@@ -346,6 +358,14 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                   if (i < nst) st_stream(dst + i * (long long)csr, f[cam][i]);
+                if (PEERS) {
+                  for (int pr = 0; pr < kp.numPeers; ++pr) {
+                    float* pv = dst + kp.peerDelta[pr];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                      if (i < nst) st_stream(pv + i * (long long)csr, f[cam][i]);
+                  }
+                }
               }
             }
           }

@@ -8,7 +8,7 @@ non-CUDA tensor or a missing library is an error.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -51,7 +51,11 @@ class SweepCall:
 
     def __init__(self, feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor], masks: Optional[Tensor],
                  rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
-                 want_valid: bool = False):
+                 want_valid: bool = False, out: Optional[Tensor] = None, cand_offset: int = 0,
+                 peer_ptrs: Sequence[int] = ()):
+        """`out`, `cand_offset`, `peer_ptrs`: candidate-sharded sweep.  `out` is the full [B, Cout, Dvol, Ho, Wo]
+        volume (contiguous); this call fills candidates [cand_offset, cand_offset + num_cands) of it and of every
+        peer-mapped volume in `peer_ptrs` (raw device pointers from sharding.PeerVolume)."""
         self.lib = abi.load_library()
         _require_cuda(feats, "feats")
         if feats.dtype != torch.float32 or feats.dim() != 5:
@@ -126,9 +130,27 @@ class SweepCall:
                 self.keep.append(gm)
 
         cout = Cc if aggregate == abi.AGG_STD else CAM * Cc
-        self.vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=torch.float32, device=feats.device)
+        if out is None:
+            if cand_offset or len(peer_ptrs):
+                raise RuntimeError("a candidate-sharded sweep needs the full volume passed as `out`")
+            self.vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=torch.float32, device=feats.device)
+        else:
+            _require_cuda(out, "out")
+            if (out.dtype != torch.float32 or out.dim() != 5 or not out.is_contiguous() or out.shape[0] != B
+                    or out.shape[1] != cout or tuple(out.shape[3:]) != (out_h, out_w)):
+                raise RuntimeError(f"`out` must be a contiguous float32 [B, {cout}, Dvol, {out_h}, {out_w}] volume")
+            if cand_offset < 0 or cand_offset + num_cands > out.shape[2]:
+                raise RuntimeError("candidate slice does not fit the output volume")
+            if len(peer_ptrs) > abi.MAX_PEERS:
+                raise RuntimeError(f"at most {abi.MAX_PEERS} peer volumes")
+            self.vol = out
+            a.cand_offset, a.vol_num_cands, a.num_peers = cand_offset, out.shape[2], len(peer_ptrs)
+            for i, ptr in enumerate(peer_ptrs):
+                a.peer_vols[i] = int(ptr)
         a.vol = self.vol.data_ptr()
         if want_valid and aggregate == abi.AGG_STD:
+            if out is not None:
+                raise RuntimeError("the validity output is not available for a candidate-sharded sweep")
             self.valid = torch.empty((B, num_cands, out_h, out_w), dtype=torch.uint8, device=feats.device)
             a.valid_out = self.valid.data_ptr()
         else:

@@ -103,6 +103,91 @@ def all_gather_candidates(local: Tensor, num_cands: int, group=None, out: Option
     return out
 
 
+class _RawCudaBuffer:
+    """Device memory owned by libmvsgi_b200 (mvsgi_p2p_alloc), exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner  # keeps the allocation alive as long as any tensor view exists
+
+
+class PeerVolume:
+    """`n_buffers` copies of a [B, C, D, Ho, Wo] float32 volume on this GPU, each also mapped into every other rank of
+    `group` (one process per GPU on one NVLink/NVSwitch box), so that a candidate-sharded sweep can store its slice
+    straight into all ranks' volumes (include/mvsgi_b200.h: MvsgiSweepArgs.peer_vols).
+
+    Buffers alternate between calls: with the per-call rendezvous of CandidateShardedSweep a rank can be at most one
+    call ahead of its peers, so two buffers are enough to keep a fast rank from overwriting a volume its neighbour
+    is still reading."""
+
+    def __init__(self, shape, device, group=None, n_buffers: int = 2):
+        import ctypes as C
+
+        from . import abi
+
+        self.lib = abi.load_library()
+        self.group = group
+        self.shape = tuple(int(v) for v in shape)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PeerVolume lives in GPU memory; there is no CPU path")
+        rank, world = _rank_world(None, None, group)
+        self.rank, self.world = rank, world
+        if world - 1 > abi.MAX_PEERS:
+            raise RuntimeError(f"at most {abi.MAX_PEERS + 1} ranks")
+        n = 1
+        for v in self.shape:
+            n *= v
+        self.stride_bytes = (n * 4 + 255) // 256 * 256
+        self.n_buffers = n_buffers
+        self._turn = 0
+        base = C.c_void_p()
+        with torch.cuda.device(self.device):
+            abi.check(self.lib.mvsgi_p2p_alloc(self.stride_bytes * n_buffers, C.byref(base)), "mvsgi_p2p_alloc")
+            self._base = base.value
+            handle = (C.c_uint8 * abi.P2P_HANDLE_BYTES)()
+            abi.check(self.lib.mvsgi_p2p_export(self._base, handle), "mvsgi_p2p_export")
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            everyone = torch.empty(world * abi.P2P_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+            if world > 1:
+                dist.all_gather_into_tensor(everyone, mine, group=group)
+            else:
+                everyone.copy_(mine)
+            everyone = everyone.cpu().numpy().reshape(world, abi.P2P_HANDLE_BYTES)
+            self._peer_bases = []
+            for r in range(world):
+                if r == rank:
+                    continue
+                h = (C.c_uint8 * abi.P2P_HANDLE_BYTES)(*[int(v) for v in everyone[r]])
+                ptr = C.c_void_p()
+                abi.check(self.lib.mvsgi_p2p_open(h, C.byref(ptr)), f"mvsgi_p2p_open(rank {r})")
+                self._peer_bases.append(ptr.value)
+        self.tensors = [torch.as_tensor(_RawCudaBuffer(self._base + i * self.stride_bytes, self.shape, self),
+                                        device=self.device) for i in range(n_buffers)]
+        if world > 1:
+            dist.barrier(group=group)  # nobody stores into a peer before everybody has mapped everybody
+
+    def next(self):
+        """(local tensor view, peer pointers) of the buffer for this call."""
+        i = self._turn
+        self._turn = (self._turn + 1) % self.n_buffers
+        return self.tensors[i], [b + i * self.stride_bytes for b in self._peer_bases]
+
+    def close(self):
+        if getattr(self, "_base", None) is None:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)  # peers have stopped storing into this allocation
+            for p in self._peer_bases:
+                self.lib.mvsgi_p2p_close(p)
+            self.tensors = []
+            self.lib.mvsgi_p2p_free(self._base)
+        self._base = None
+
+
 class CandidateShardedSweep(torch.nn.Module):
     """Candidate-sharded front-end of a std / concat sweep module (modules.SphericalSweepStdMasked / SphericalSweep).
 
@@ -110,10 +195,15 @@ class CandidateShardedSweep(torch.nn.Module):
     in-kernel projection from a sub-rig, or a slice of the supplied grids) and `all_gather_candidates` rebuilds
     the volume.  `post_vol` runs afterwards on the full volume, as in the reference forward()."""
 
-    def __init__(self, builder: torch.nn.Module, rig: Optional[Rig] = None, group=None):
+    def __init__(self, builder: torch.nn.Module, rig: Optional[Rig] = None, group=None, fused: bool = False):
+        """fused=True: no collective afterwards -- the sweep kernel stores every voxel of its slice into all ranks'
+        volumes over NVLink (PeerVolume) and a one-element all-reduce on the stream is the only rendezvous."""
         super().__init__()
         self.builder = builder
         self.group = group
+        self.fused = fused
+        self._peer_volume: Optional[PeerVolume] = None
+        self._flag: Optional[Tensor] = None
         self.full_rig = rig
         self.num_cands = rig.num_cands if rig is not None else None
         if rig is not None:
@@ -134,11 +224,44 @@ class CandidateShardedSweep(torch.nn.Module):
             d0, d1 = balanced_range(D, rank, world)
             g = grids[:, :, d0:d1]
             gm = grid_masks[:, :, d0:d1] if grid_masks is not None else None
+        if self.fused:
+            return self._sweep_fused(feats, g, gm, masks, D)
         if hasattr(self.builder, "sweep_with_valid"):
             local = self.builder.sweep(feats, g, gm, masks)
         else:
             local = self.builder.sweep(feats, g, masks)
         return all_gather_candidates(local, D, self.group)
+
+    def _sweep_fused(self, feats, g, gm, masks, D):
+        from . import abi, ops
+
+        rank, world = _rank_world(None, None, self.group)
+        d0, d1 = balanced_range(D, rank, world)
+        b = self.builder
+        std = b._aggregate == abi.AGG_STD
+        B, CAM, Cc = feats.shape[:3]
+        cout = Cc if std else CAM * Cc
+        if self.full_rig is not None:
+            Ho, Wo = self.full_rig.cv_camera.H, self.full_rig.cv_camera.W
+        else:
+            Ho, Wo = g.shape[3:5]
+        shape = (B, cout, D, Ho, Wo)
+        if self._peer_volume is None or self._peer_volume.shape != shape:
+            if self._peer_volume is not None:
+                self._peer_volume.close()
+            self._peer_volume = PeerVolume(shape, feats.device, self.group)
+            self._flag = torch.zeros(1, device=feats.device)
+        vol, peers = self._peer_volume.next()
+        if std and b._static_masks is not None:
+            masks = b._static_masks
+        call = ops.SweepCall(feats, g, gm, masks if std else None, b._rig_blob, b._aggregate, Ho, Wo, d1 - d0,
+                             out=vol, cand_offset=d0, peer_ptrs=peers)
+        call.run()
+        if world > 1:
+            # stream-ordered rendezvous: it starts after this rank's sweep kernel and ends when every rank has joined,
+            # i.e. when every rank's stores into this volume have been issued and their kernels have completed
+            dist.all_reduce(self._flag, group=self.group)
+        return vol
 
     def forward(self, feats, grids, grid_masks, masks):
         return self.builder.post_vol(self.sweep(feats, grids, grid_masks, masks))

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--workload", default="HIGHD")
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--small", action="store_true", help="shrunken shapes (tests)")
     args = ap.parse_args()
     from mvs_gi_b200 import modules, sharding, synthetic
 
@@ -34,6 +35,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     w = synthetic.WORKLOADS[args.workload]
+    if args.small:
+        w = synthetic.small(w, feat_hw=(32, 128), mask_hw=(128, 512), cv_hw=(20, 80), n_cands=7)
     rig = w.rig()
     B = args.batch
     gen = torch.Generator(device=dev).manual_seed(4321)  # same features on every rank
@@ -43,6 +46,8 @@ def main():
     full = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval().attach_rig(rig)
     shard = sharding.CandidateShardedSweep(
         modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval(), rig)
+    fused = sharding.CandidateShardedSweep(
+        modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval(), rig, fused=True)
     d0, d1 = sharding.candidate_shard(w.num_cands)
 
     def timed(fn, n):
@@ -65,7 +70,11 @@ def main():
         local_vol, ms_local = timed(lambda: shard.builder.sweep(feats, None, None, masks), args.steps)
         _, ms_gather = timed(lambda: sharding.all_gather_candidates(local_vol, w.num_cands), args.steps)
         vol_full, ms_full = timed(lambda: full.sweep(feats, None, None, masks), args.steps)
-    same = bool(torch.equal(vol_sharded, vol_full))
+        vol_fused, ms_fused = timed(lambda: fused.sweep(feats, None, None, masks), args.steps)
+        # local compute of the fused call without its peers' traffic cannot be separated; time the rendezvous alone
+        flag = torch.zeros(1, device=dev)
+        _, ms_rdv = timed(lambda: dist.all_reduce(flag), args.steps)
+    same = bool(torch.equal(vol_sharded, vol_full)) and bool(torch.equal(vol_fused, vol_full))
     ok = torch.tensor([1 if same else 0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -75,10 +84,13 @@ def main():
             "what": "candidate-sharded sweep", "workload": w.name, "n_gpus": world, "batch": B,
             "bit_identical_to_unsharded_on_all_ranks": bool(ok.item()),
             "ms_unsharded_one_gpu": ms_full, "ms_sharded_total": ms_sharded, "ms_local_slice_sweep": ms_local,
-            "ms_allgather_and_reassemble": ms_gather, "vol_mbytes": vol_bytes / 1e6,
+            "ms_allgather_and_reassemble": ms_gather, "ms_fused_p2p_total": ms_fused, "ms_rendezvous_allreduce": ms_rdv,
+            "nvlink_send_gbs_per_rank_fused": recv / (ms_fused * 1e-3) / 1e9, "vol_mbytes": vol_bytes / 1e6,
             "nvlink_recv_gbs_per_rank": recv / (ms_gather * 1e-3) / 1e9,
             "candidates_rank0": [d0, d1],
         }), flush=True)
+    if fused._peer_volume is not None:
+        fused._peer_volume.close()
     dist.destroy_process_group()
     if not same:
         sys.exit(1)
