@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MVSGI_ABI_VERSION 4
+#define MVSGI_ABI_VERSION 5
 #define MVSGI_MAX_CAMS 4
 #define MVSGI_MAX_CANDS 64
 #define MVSGI_MAX_PEERS 7 /* extra destinations of a candidate-sharded sweep (8 GPUs of one box) */
@@ -215,6 +215,48 @@ typedef struct MvsgiSoftArgminArgs {
   int32_t* argmax;         /* [B, out_h, out_w] first-max candidate index, or NULL */
 } MvsgiSoftArgminArgs;
 int mvsgi_softargmin_f32(const MvsgiSoftArgminArgs* args, void* cuda_stream);
+
+/* ---- backward passes (training drop-in) ------------------------------------ */
+/* What torch.autograd derives from the reference's forward code when
+ * training_step differentiates through cv_builder and dist_regressor
+ * (dsta_mvs/model/mvs_model/spherical_sweep_stereo.py:170-202,
+ *  spherical_sweep_stereo_2024.py:97-143).  Only `feats` / `costs` receive
+ * gradients; grids, masks and the candidate list are data, as in the reference
+ * (dataset tensors, no requires_grad). */
+
+/* d sum(grad_vol * vol) / d feats of mvsgi_sweep_f32 for the problem `fwd` describes.
+ * Replaces the autograd graph of SphericalSweepStdMasked.sweep (spherical_sweep_avg.py:38-136) /
+ * SphericalSweep.sweep (spherical_sweep.py:38-68) incl. the sampler's gather backward (backports.py:76-86).
+ * Of `fwd`, the fields vol, valid_out, peer_vols, num_peers, flags, workspace and workspace_bytes are ignored
+ * (cand_offset / vol_num_cands are honoured: grad_vol is then the full [B, Cout, vol_num_cands, Ho, Wo] tensor).
+ * The call re-stages feats and masks, accumulates with vector atomics into a staged gradient image and writes
+ * grad_feats (overwritten, not accumulated).  Summation order is not deterministic (fp32 atomics). */
+typedef struct MvsgiSweepBwdArgs {
+  uint32_t struct_size; /* = sizeof(MvsgiSweepBwdArgs) */
+  uint32_t flags;       /* 0 */
+  const MvsgiSweepArgs* fwd; /* HOST pointer */
+  const float* grad_vol;     /* [B, Cout, Dvol, Ho, Wo] contiguous */
+  float* grad_feats;         /* [B, CAM, C, Hf, Wf] */
+  int64_t grad_feats_stride[5]; /* B, CAM, C, H, W */
+  void* workspace;           /* >= mvsgi_sweep_backward_workspace_bytes(args), 256-byte aligned */
+  int64_t workspace_bytes;
+} MvsgiSweepBwdArgs;
+int64_t mvsgi_sweep_backward_workspace_bytes(const MvsgiSweepBwdArgs* args);
+int mvsgi_sweep_backward_f32(const MvsgiSweepBwdArgs* args, void* cuda_stream);
+
+/* Backward of mvsgi_softargmin_f32 wrt costs[:, 0] (distance_regressor.py:51-80: F.interpolate, F.softmax,
+ * sum(norm_costs * inv_dist_idx)).  Of `fwd`, inv_dist / norm_costs / argmax are ignored.  Either upstream gradient
+ * may be NULL (that output was not used).  grad_costs is overwritten; element (b, d, y, x) at the given strides. */
+typedef struct MvsgiSoftArgminBwdArgs {
+  uint32_t struct_size;
+  uint32_t flags;
+  const MvsgiSoftArgminArgs* fwd; /* HOST pointer */
+  const float* grad_inv_dist;     /* [B, 1, out_h, out_w] contiguous, or NULL */
+  const float* grad_norm_costs;   /* [B, D, out_h, out_w] contiguous, or NULL */
+  float* grad_costs;
+  int64_t grad_costs_stride[4];   /* B, D, H, W */
+} MvsgiSoftArgminBwdArgs;
+int mvsgi_softargmin_backward_f32(const MvsgiSoftArgminBwdArgs* args, void* cuda_stream);
 
 /* ---- peer-mapped volumes for the candidate-sharded sweep ------------------- */
 /* One process per GPU.  Each rank allocates its copy of the volume with mvsgi_p2p_alloc (cudaMalloc on the current

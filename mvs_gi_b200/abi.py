@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_CAMS = 4
 MAX_CANDS = 64
 MAX_PEERS = 7
@@ -125,6 +125,31 @@ class MvsgiSoftArgminArgs(C.Structure):
     ]
 
 
+class MvsgiSweepBwdArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("fwd", C.POINTER(MvsgiSweepArgs)),
+        ("grad_vol", C.c_void_p),
+        ("grad_feats", C.c_void_p),
+        ("grad_feats_stride", C.c_int64 * 5),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
+    ]
+
+
+class MvsgiSoftArgminBwdArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("fwd", C.POINTER(MvsgiSoftArgminArgs)),
+        ("grad_inv_dist", C.c_void_p),
+        ("grad_norm_costs", C.c_void_p),
+        ("grad_costs", C.c_void_p),
+        ("grad_costs_stride", C.c_int64 * 4),
+    ]
+
+
 # Every symbol include/mvsgi_b200.h declares: name -> (restype, argtypes).
 EXPORTS = {
     "mvsgi_sweep_workspace_bytes": (C.c_int64, [C.POINTER(MvsgiSweepArgs)]),
@@ -138,6 +163,9 @@ EXPORTS = {
          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
     "mvsgi_softargmin_f32": (C.c_int, [C.POINTER(MvsgiSoftArgminArgs), C.c_void_p]),
+    "mvsgi_sweep_backward_workspace_bytes": (C.c_int64, [C.POINTER(MvsgiSweepBwdArgs)]),
+    "mvsgi_sweep_backward_f32": (C.c_int, [C.POINTER(MvsgiSweepBwdArgs), C.c_void_p]),
+    "mvsgi_softargmin_backward_f32": (C.c_int, [C.POINTER(MvsgiSoftArgminBwdArgs), C.c_void_p]),
     "mvsgi_p2p_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "mvsgi_p2p_free": (C.c_int, [C.c_void_p]),
     "mvsgi_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -8,6 +8,7 @@
 #include "softargmin.cuh"
 #include "stage.cuh"
 #include "sweep.cuh"
+#include "backward.cuh"
 
 namespace {
 
@@ -139,6 +140,48 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   return MVSGI_OK;
 }
 
+// Kernel parameters of the sweep (shared by the forward and the backward kernels).
+void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint32_t* ws_bits, mvsgi::SweepKP& kp) {
+  const bool std_agg = a->aggregate == MVSGI_AGG_STD;
+  const int Wp = a->feat_w + 2, Hp1 = a->feat_h + 3;
+  memset(&kp, 0, sizeof(kp));
+  kp.B = a->batch; kp.C = a->feat_chs; kp.D = a->num_cands; kp.Cout = p.cout; kp.CG = p.cg;
+  kp.Ho = a->out_h; kp.Wo = a->out_w; kp.Hf = a->feat_h; kp.Wf = a->feat_w; kp.Hm = a->mask_h; kp.Wm = a->mask_w;
+  kp.P = a->out_h * a->out_w; kp.numRuns = p.num_runs; kp.runLen = p.run_len; kp.dch = p.dch;
+  kp.numChunks = p.num_chunks; kp.numItems = p.num_items; kp.maxPairs = p.max_pairs; kp.grpPx = p.group_px; kp.interleave = p.interleave;
+  kp.feat = ws_feats;
+  kp.fsY = Wp * mvsgi::kCG;
+  kp.fsCg = Hp1 * kp.fsY;
+  kp.fsCam = kp.fsCg * p.cg;
+  kp.fsB = (long long)kp.fsCam * a->num_cams;
+  kp.zeroOff = (a->feat_h + 1) * kp.fsY;  // rows Hf+1 and Hf+2 are all zero
+  if (p.pack_masks) {
+    kp.mbits = ws_bits;
+    kp.mPitch = p.mask_pitch;
+    kp.mbCam = p.mask_words;
+    kp.mbB = kp.mbCam * a->num_cams;
+    kp.perFrameMasks = p.per_frame_masks ? 1 : 0;
+  }
+  kp.gridMode = a->grid_mode;
+  kp.perFrameGrids = p.per_frame_grids ? 1 : 0;
+  if (a->grid_mode == MVSGI_GRID_SUPPLIED) {
+    kp.grids = a->grids;
+    kp.gsB = a->grids_stride[0]; kp.gsCam = a->grids_stride[1]; kp.gsD = a->grids_stride[2];
+    kp.gsY = a->grids_stride[3]; kp.gsX = a->grids_stride[4];
+    if (std_agg) {
+      kp.gmask = a->grid_masks;
+      kp.gmB = a->grid_masks_stride[0]; kp.gmCam = a->grid_masks_stride[1]; kp.gmD = a->grid_masks_stride[2];
+      kp.gmY = a->grid_masks_stride[3]; kp.gmX = a->grid_masks_stride[4];
+    }
+  }
+  kp.vol = a->vol;
+  kp.validOut = std_agg ? a->valid_out : nullptr;
+  kp.dOff = a->cand_offset;
+  kp.Dvol = a->vol_num_cands > 0 ? a->vol_num_cands : a->num_cands;
+  kp.numPeers = a->num_peers;
+  for (int i = 0; i < a->num_peers; ++i) kp.peerDelta[i] = (long long)((reinterpret_cast<intptr_t>(a->peer_vols[i]) - reinterpret_cast<intptr_t>(a->vol)) / 4);
+}
+
 template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS = false>
 cudaError_t launch_sweep(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
   auto kern = mvsgi::sweep_kernel<CAM, AGG, FULLC, VALID, PEERS>;
@@ -210,6 +253,38 @@ void launch_softargmin_x2(const mvsgi::SoftKP& kp, dim3 grid, cudaStream_t st) {
   else if (kp.D == 8) launch_x2_flags<8, true>(kp, grid, st);
   else if (kp.D < 8) launch_x2_flags<8, false>(kp, grid, st);
   else launch_x2_flags<16, false>(kp, grid, st);
+}
+
+}  // namespace
+
+namespace {
+
+// the forward problem as the backward sees it: no outputs, no peers, workspace laid out by the forward plan
+int backward_plan(const MvsgiSweepBwdArgs* a, MvsgiSweepArgs* f, SweepPlan* p) {
+  if (a == nullptr || a->fwd == nullptr) return MVSGI_E_NULL;
+  if (a->struct_size != sizeof(MvsgiSweepBwdArgs)) return MVSGI_E_VERSION;
+  if (a->flags != 0) return MVSGI_E_UNSUPPORTED;
+  if (a->grad_vol == nullptr || a->grad_feats == nullptr) return MVSGI_E_NULL;
+  *f = *a->fwd;
+  f->vol = const_cast<float*>(a->grad_vol);  // only has to be non-NULL for validation; never written
+  f->valid_out = nullptr;
+  f->num_peers = 0;
+  f->flags = 0;
+  return validate_and_plan(f, p);
+}
+
+template <int AGG>
+cudaError_t launch_sweep_backward(int cams, const mvsgi::SweepBwdKP& kb, const MvsgiRig& rig, cudaStream_t st) {
+  const int P = kb.f.P;
+  dim3 grid((P + mvsgi::kBwdThreads / 4 - 1) / (mvsgi::kBwdThreads / 4), kb.f.D, kb.f.B);
+  switch (cams) {
+    case 1: mvsgi::sweep_backward_kernel<1, AGG><<<grid, mvsgi::kBwdThreads, 0, st>>>(kb, rig); break;
+    case 2: mvsgi::sweep_backward_kernel<2, AGG><<<grid, mvsgi::kBwdThreads, 0, st>>>(kb, rig); break;
+    case 3: mvsgi::sweep_backward_kernel<3, AGG><<<grid, mvsgi::kBwdThreads, 0, st>>>(kb, rig); break;
+    default: mvsgi::sweep_backward_kernel<4, AGG><<<grid, mvsgi::kBwdThreads, 0, st>>>(kb, rig); break;
+  }
+  g_launches++;
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -305,42 +380,7 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
   // 3. the sweep
   if (!do_sweep) return MVSGI_OK;
   mvsgi::SweepKP kp;
-  memset(&kp, 0, sizeof(kp));
-  kp.B = a->batch; kp.C = a->feat_chs; kp.D = a->num_cands; kp.Cout = p.cout; kp.CG = p.cg;
-  kp.Ho = a->out_h; kp.Wo = a->out_w; kp.Hf = a->feat_h; kp.Wf = a->feat_w; kp.Hm = a->mask_h; kp.Wm = a->mask_w;
-  kp.P = a->out_h * a->out_w; kp.numRuns = p.num_runs; kp.runLen = p.run_len; kp.dch = p.dch;
-  kp.numChunks = p.num_chunks; kp.numItems = p.num_items; kp.maxPairs = p.max_pairs; kp.grpPx = p.group_px; kp.interleave = p.interleave;
-  kp.feat = ws_feats;
-  kp.fsY = Wp * mvsgi::kCG;
-  kp.fsCg = Hp1 * kp.fsY;
-  kp.fsCam = kp.fsCg * p.cg;
-  kp.fsB = (long long)kp.fsCam * a->num_cams;
-  kp.zeroOff = (a->feat_h + 1) * kp.fsY;  // rows Hf+1 and Hf+2 are all zero
-  if (p.pack_masks) {
-    kp.mbits = ws_bits;
-    kp.mPitch = p.mask_pitch;
-    kp.mbCam = p.mask_words;
-    kp.mbB = kp.mbCam * a->num_cams;
-    kp.perFrameMasks = p.per_frame_masks ? 1 : 0;
-  }
-  kp.gridMode = a->grid_mode;
-  kp.perFrameGrids = p.per_frame_grids ? 1 : 0;
-  if (a->grid_mode == MVSGI_GRID_SUPPLIED) {
-    kp.grids = a->grids;
-    kp.gsB = a->grids_stride[0]; kp.gsCam = a->grids_stride[1]; kp.gsD = a->grids_stride[2];
-    kp.gsY = a->grids_stride[3]; kp.gsX = a->grids_stride[4];
-    if (std_agg) {
-      kp.gmask = a->grid_masks;
-      kp.gmB = a->grid_masks_stride[0]; kp.gmCam = a->grid_masks_stride[1]; kp.gmD = a->grid_masks_stride[2];
-      kp.gmY = a->grid_masks_stride[3]; kp.gmX = a->grid_masks_stride[4];
-    }
-  }
-  kp.vol = a->vol;
-  kp.validOut = std_agg ? a->valid_out : nullptr;
-  kp.dOff = a->cand_offset;
-  kp.Dvol = a->vol_num_cands > 0 ? a->vol_num_cands : a->num_cands;
-  kp.numPeers = a->num_peers;
-  for (int i = 0; i < a->num_peers; ++i) kp.peerDelta[i] = (long long)((reinterpret_cast<intptr_t>(a->peer_vols[i]) - reinterpret_cast<intptr_t>(a->vol)) / 4);
+  fill_kp(a, p, ws_feats, ws_bits, kp);
 
   MvsgiRig rig;
   if (a->grid_mode == MVSGI_GRID_PROJECT) rig = *a->rig;
@@ -360,6 +400,97 @@ int mvsgi_project_only_f32(const MvsgiProjectArgs* a, void* stream) {
     return MVSGI_E_SHAPE;
   const int n = r.cv_width * r.cv_height;
   mvsgi::project_only_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r, a->grids, a->grid_masks);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+// ---- backward passes -------------------------------------------------------------------------------------------------
+
+int64_t mvsgi_sweep_backward_workspace_bytes(const MvsgiSweepBwdArgs* a) {
+  MvsgiSweepArgs f;
+  SweepPlan p;
+  const int rc = backward_plan(a, &f, &p);
+  return rc != MVSGI_OK ? (int64_t)rc : p.total_bytes + p.feats_bytes;
+}
+
+int mvsgi_sweep_backward_f32(const MvsgiSweepBwdArgs* a, void* stream) {
+  MvsgiSweepArgs f;
+  SweepPlan p;
+  int rc = backward_plan(a, &f, &p);
+  if (rc != MVSGI_OK) return rc;
+  if (a->workspace == nullptr) return MVSGI_E_NULL;
+  if (a->workspace_bytes < p.total_bytes + p.feats_bytes || (reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0)
+    return MVSGI_E_WORKSPACE;
+  if (f.batch > 65535 || f.num_cands > 65535 || f.feat_h > 65535) return MVSGI_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)a->workspace;
+  // 1. stage feats + pack masks exactly as the forward does
+  f.workspace = ws;
+  f.workspace_bytes = p.total_bytes;
+  f.flags = MVSGI_FLAG_STAGE_ONLY;
+  rc = mvsgi_sweep_f32(&f, stream);
+  if (rc != MVSGI_OK) return rc;
+  // 2. zero the staged gradient image
+  float* gstage = (float*)(ws + p.total_bytes);
+  cudaError_t e = cudaMemsetAsync(gstage, 0, (size_t)p.feats_bytes, st);
+  if (e != cudaSuccess) return (int)e;
+  // 3. scatter
+  mvsgi::SweepBwdKP kb;
+  fill_kp(&f, p, (float*)ws, (uint32_t*)(ws + p.feats_bytes), kb.f);
+  kb.gradVol = a->grad_vol;
+  kb.gradStage = gstage;
+  MvsgiRig rig;
+  if (f.grid_mode == MVSGI_GRID_PROJECT) rig = *f.rig;
+  else memset(&rig, 0, sizeof(rig));
+  e = f.aggregate == MVSGI_AGG_STD ? launch_sweep_backward<MVSGI_AGG_STD>(f.num_cams, kb, rig, st)
+                                   : launch_sweep_backward<MVSGI_AGG_CONCAT>(f.num_cams, kb, rig, st);
+  if (e != cudaSuccess) return (int)e;
+  // 4. staged gradient -> grad_feats
+  const int N = f.batch * f.num_cams;
+  const int x_blocks = (f.feat_w + mvsgi::kStagePx - 1) / mvsgi::kStagePx;
+  if ((int64_t)N * p.cg * x_blocks >= (1ll << 31)) return MVSGI_E_SHAPE;
+  dim3 grid((unsigned)(N * p.cg * x_blocks), f.feat_h);
+  mvsgi::unstage_grad_kernel<<<grid, 256, 0, st>>>(gstage, f.num_cams, f.feat_chs, p.cg, f.feat_h, f.feat_w,
+                                                   a->grad_feats, a->grad_feats_stride[0], a->grad_feats_stride[1],
+                                                   a->grad_feats_stride[2], a->grad_feats_stride[3],
+                                                   a->grad_feats_stride[4]);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int mvsgi_softargmin_backward_f32(const MvsgiSoftArgminBwdArgs* a, void* stream) {
+  if (a == nullptr || a->fwd == nullptr) return MVSGI_E_NULL;
+  if (a->struct_size != sizeof(MvsgiSoftArgminBwdArgs)) return MVSGI_E_VERSION;
+  if (a->flags != 0) return MVSGI_E_UNSUPPORTED;
+  const MvsgiSoftArgminArgs* f = a->fwd;
+  if (f->struct_size != sizeof(MvsgiSoftArgminArgs)) return MVSGI_E_VERSION;
+  if (f->costs == nullptr || f->inv_dist_idx == nullptr || a->grad_costs == nullptr) return MVSGI_E_NULL;
+  if (f->batch < 1 || f->num_cands < 1 || f->num_cands > MVSGI_MAX_CANDS || f->in_h < 1 || f->in_w < 1 ||
+      f->out_h < 1 || f->out_w < 1 || f->batch > 65535 || f->out_h > 65535)
+    return MVSGI_E_SHAPE;
+  mvsgi::SoftBwdKP kb;
+  mvsgi::SoftKP& kp = kb.f;
+  kp.B = f->batch; kp.D = f->num_cands; kp.Hin = f->in_h; kp.Win = f->in_w; kp.Hout = f->out_h; kp.Wout = f->out_w;
+  kp.interp = (f->out_h != f->in_h || f->out_w != f->in_w) ? 1 : 0;
+  kp.scaleH = f->src_scale_h; kp.scaleW = f->src_scale_w;
+  kp.costs = f->costs;
+  kp.sB = f->costs_stride[0]; kp.sD = f->costs_stride[1]; kp.sY = f->costs_stride[2]; kp.sX = f->costs_stride[3];
+  kp.idx = f->inv_dist_idx; kp.invDist = nullptr; kp.normCosts = nullptr; kp.argmax = nullptr;
+  kb.gInv = a->grad_inv_dist; kb.gNc = a->grad_norm_costs; kb.gradCosts = a->grad_costs;
+  kb.gB = a->grad_costs_stride[0]; kb.gD = a->grad_costs_stride[1]; kb.gY = a->grad_costs_stride[2];
+  kb.gX = a->grad_costs_stride[3];
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kp.interp) {  // the upsample's adjoint accumulates with atomics
+    const long long total = (long long)kp.B * kp.D * kp.Hin * kp.Win;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    mvsgi::zero_strided4_kernel<<<blocks, 256, 0, st>>>(a->grad_costs, kp.B, kp.D, kp.Hin, kp.Win, kb.gB, kb.gD, kb.gY,
+                                                        kb.gX);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 grid((kp.Wout + 127) / 128, kp.Hout, kp.B);
+  mvsgi::softargmin_backward_kernel<<<grid, 128, 0, st>>>(kb);
   g_launches++;
   return (int)cudaGetLastError();
 }

@@ -49,13 +49,6 @@ class _ConvBlk3d(nn.Module):
         return self.activation(self.norm_layer(self.conv_layer(x)))
 
 
-def _reject_autograd(feats: Tensor) -> None:
-    if torch.is_grad_enabled() and feats.requires_grad:
-        raise NotImplementedError(
-            "mvs_gi_b200: the fused sweep is forward-only (SURVEY.md §8 row f1 'backward' is not built yet); "
-            "wrap inference in torch.no_grad() or keep the reference module for training")
-
-
 class _SweepBase(nn.Module):
     _aggregate = abi.AGG_STD
 
@@ -99,7 +92,6 @@ class _SweepBase(nn.Module):
         return new.to(next(module.parameters()).device)
 
     def _run(self, feats: Tensor, grids, grid_masks, masks, want_valid: bool = False):
-        _reject_autograd(feats)
         if feats.shape[1] != self.num_cams:
             raise RuntimeError(f"expected {self.num_cams} cameras, feats has {feats.shape[1]}")
         if self._rig_blob is not None:
@@ -186,7 +178,6 @@ class DistanceRegressorWithFixedCandidates(nn.Module):
         return H, W, 1.0
 
     def regress(self, costs: Tensor, want_norm_costs: bool = True, want_argmax: bool = False):
-        _reject_autograd(costs)
         H, W = costs.shape[-2:]
         Ho, Wo, scale = self._out_size(H, W)
         return ops.softargmin_op(costs, self.inv_dist_idx, Ho, Wo, float(scale), want_norm_costs, want_argmax)

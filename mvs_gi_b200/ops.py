@@ -52,10 +52,12 @@ class SweepCall:
     def __init__(self, feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor], masks: Optional[Tensor],
                  rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
                  want_valid: bool = False, out: Optional[Tensor] = None, cand_offset: int = 0,
-                 peer_ptrs: Sequence[int] = ()):
+                 peer_ptrs: Sequence[int] = (), describe_only: bool = False):
         """`out`, `cand_offset`, `peer_ptrs`: candidate-sharded sweep.  `out` is the full [B, Cout, Dvol, Ho, Wo]
         volume (contiguous); this call fills candidates [cand_offset, cand_offset + num_cands) of it and of every
-        peer-mapped volume in `peer_ptrs` (raw device pointers from sharding.PeerVolume)."""
+        peer-mapped volume in `peer_ptrs` (raw device pointers from sharding.PeerVolume).
+        `describe_only`: fill the argument struct (inputs only) without allocating the volume or the workspace —
+        how the backward op describes the forward problem to mvsgi_sweep_backward_f32."""
         self.lib = abi.load_library()
         _require_cuda(feats, "feats")
         if feats.dtype != torch.float32 or feats.dim() != 5:
@@ -130,6 +132,9 @@ class SweepCall:
                 self.keep.append(gm)
 
         cout = Cc if aggregate == abi.AGG_STD else CAM * Cc
+        self.args = a
+        if describe_only:
+            return
         if out is None:
             if cand_offset or len(peer_ptrs):
                 raise RuntimeError("a candidate-sharded sweep needs the full volume passed as `out`")
@@ -238,6 +243,131 @@ def _(costs, inv_dist_idx, out_h, out_w, src_scale, want_norm_costs, want_argmax
     return (costs.new_empty((B, 1, out_h, out_w)),
             costs.new_empty((B, D, out_h, out_w) if want_norm_costs else (0,)),
             costs.new_empty((B, out_h, out_w) if want_argmax else (0,), dtype=torch.int32))
+
+
+# ---- backward ---------------------------------------------------------------------------------
+@torch.library.custom_op("mvsgi::sweep_backward", mutates_args=())
+def sweep_backward_op(grad_vol: Tensor, feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor],
+                      masks: Optional[Tensor], rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int,
+                      num_cands: int) -> Tensor:
+    """d sum(grad_vol * sweep(feats, ...)) / d feats  (autograd of spherical_sweep_avg.py:38-136 / spherical_sweep.py:38-68)."""
+    lib = abi.load_library()
+    _require_cuda(grad_vol, "grad_vol")
+    fwd = SweepCall(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands,
+                    describe_only=True)
+    B, CAM, Cc = feats.shape[:3]
+    cout = Cc if aggregate == abi.AGG_STD else CAM * Cc
+    if tuple(grad_vol.shape) != (B, cout, num_cands, out_h, out_w) or grad_vol.dtype != torch.float32:
+        raise RuntimeError(f"grad_vol must be float32 [{B}, {cout}, {num_cands}, {out_h}, {out_w}]")
+    grad_vol = grad_vol.contiguous()
+    grad_feats = torch.empty_like(feats, memory_format=torch.contiguous_format)
+    b = abi.MvsgiSweepBwdArgs()
+    b.struct_size = C.sizeof(abi.MvsgiSweepBwdArgs)
+    b.fwd = C.pointer(fwd.args)
+    b.grad_vol = grad_vol.data_ptr()
+    b.grad_feats = grad_feats.data_ptr()
+    _fill_strides(b.grad_feats_stride, grad_feats.stride())
+    need = lib.mvsgi_sweep_backward_workspace_bytes(C.byref(b))
+    if need < 0:
+        abi.check(int(need), "mvsgi_sweep_backward_workspace_bytes")
+    ws = torch.empty((max(int(need), 256),), dtype=torch.uint8, device=feats.device)
+    b.workspace, b.workspace_bytes = ws.data_ptr(), ws.numel()
+    with torch.cuda.device(feats.device):
+        abi.check(lib.mvsgi_sweep_backward_f32(C.byref(b), _stream_ptr(feats.device)), "mvsgi_sweep_backward_f32")
+    return grad_feats
+
+
+@sweep_backward_op.register_fake
+def _(grad_vol, feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands):
+    return torch.empty_like(feats, memory_format=torch.contiguous_format)
+
+
+def _sweep_setup(ctx, inputs, output):
+    feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, _ = inputs
+    ctx.save_for_backward(feats, grids, grid_masks, masks, rig_blob)
+    ctx.meta = (aggregate, out_h, out_w, num_cands)
+
+
+def _sweep_bwd(ctx, grad_vol, grad_valid):
+    feats, grids, grid_masks, masks, rig_blob = ctx.saved_tensors
+    gf = None
+    if ctx.needs_input_grad[0] and grad_vol is not None:
+        gf = sweep_backward_op(grad_vol, feats, grids, grid_masks, masks, rig_blob, *ctx.meta)
+    return gf, None, None, None, None, None, None, None, None, None
+
+
+sweep_op.register_autograd(_sweep_bwd, setup_context=_sweep_setup)
+
+
+def _softargmin_args(costs: Tensor, idx: Tensor, out_h: int, out_w: int, src_scale: float) -> abi.MvsgiSoftArgminArgs:
+    B, _, D, H, W = costs.shape
+    a = abi.MvsgiSoftArgminArgs()
+    a.struct_size = C.sizeof(abi.MvsgiSoftArgminArgs)
+    a.batch, a.num_cands, a.in_h, a.in_w, a.out_h, a.out_w = B, D, H, W, out_h, out_w
+    a.src_scale_h = a.src_scale_w = src_scale
+    a.costs = costs.data_ptr()
+    cs = costs.stride()
+    _fill_strides(a.costs_stride, (cs[0], cs[2], cs[3], cs[4]))
+    a.inv_dist_idx = idx.data_ptr()
+    return a
+
+
+@torch.library.custom_op("mvsgi::softargmin_backward", mutates_args=())
+def softargmin_backward_op(grad_inv: Optional[Tensor], grad_nc: Optional[Tensor], costs: Tensor, inv_dist_idx: Tensor,
+                           out_h: int, out_w: int, src_scale: float) -> Tensor:
+    """Gradient of softargmin wrt costs (only channel 0 of dim 1 is read by the forward, distance_regressor.py:52)."""
+    lib = abi.load_library()
+    _require_cuda(costs, "costs")
+    B, Cc, D, H, W = costs.shape
+    idx = inv_dist_idx.reshape(-1).to(device=costs.device, dtype=torch.float32).contiguous()
+    gc = (torch.zeros if Cc > 1 else torch.empty)((B, Cc, D, H, W), dtype=torch.float32, device=costs.device)
+    fwd = _softargmin_args(costs, idx, out_h, out_w, src_scale)
+    b = abi.MvsgiSoftArgminBwdArgs()
+    b.struct_size = C.sizeof(abi.MvsgiSoftArgminBwdArgs)
+    b.fwd = C.pointer(fwd)
+    keep = []
+    for name, g, shape in (("grad_inv_dist", grad_inv, (B, 1, out_h, out_w)), ("grad_norm_costs", grad_nc, (B, D, out_h, out_w))):
+        if g is None:
+            continue
+        if tuple(g.shape) != shape or g.dtype != torch.float32:
+            raise RuntimeError(f"{name} must be float32 {shape}, got {tuple(g.shape)}")
+        g = g.contiguous()
+        keep.append(g)
+        setattr(b, name, g.data_ptr())
+    b.grad_costs = gc.data_ptr()
+    gs = gc.stride()
+    _fill_strides(b.grad_costs_stride, (gs[0], gs[2], gs[3], gs[4]))
+    with torch.cuda.device(costs.device):
+        abi.check(lib.mvsgi_softargmin_backward_f32(C.byref(b), _stream_ptr(costs.device)),
+                  "mvsgi_softargmin_backward_f32")
+    return gc
+
+
+@softargmin_backward_op.register_fake
+def _(grad_inv, grad_nc, costs, inv_dist_idx, out_h, out_w, src_scale):
+    return torch.empty_like(costs, memory_format=torch.contiguous_format)
+
+
+def _softargmin_setup(ctx, inputs, output):
+    costs, inv_dist_idx, out_h, out_w, src_scale, want_nc, _ = inputs
+    ctx.save_for_backward(costs, inv_dist_idx)
+    ctx.meta = (out_h, out_w, src_scale, want_nc)
+    try:
+        ctx.set_materialize_grads(False)  # an unused output then arrives as None instead of a zero tensor
+    except Exception:
+        pass
+
+
+def _softargmin_bwd(ctx, g_inv, g_nc, g_am):
+    costs, idx = ctx.saved_tensors
+    out_h, out_w, src_scale, want_nc = ctx.meta
+    if not ctx.needs_input_grad[0] or (g_inv is None and (g_nc is None or not want_nc)):
+        return None, None, None, None, None, None, None
+    gc = softargmin_backward_op(g_inv, g_nc if want_nc else None, costs, idx, out_h, out_w, src_scale)
+    return gc, None, None, None, None, None, None
+
+
+softargmin_op.register_autograd(_softargmin_bwd, setup_context=_softargmin_setup)
 
 
 def project_only(rig_struct: abi.MvsgiRig, device) -> Tuple[Tensor, Tensor]:

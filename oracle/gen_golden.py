@@ -189,12 +189,49 @@ def case_geometry():
     (OUT / "geom_meta.json").write_text(json.dumps(meta, indent=1))
 
 
+def case_backward():
+    """gradients torch.autograd derives from the reference's forward code, on the inputs of the
+    forward fixtures (which must exist already) and seeded upstream gradients.  Own RNG: does not disturb the others."""
+    gen = np.random.default_rng(20261018)
+    for name, kind in (("std3", "std"), ("std4", "std"), ("concat3", "concat")):
+        z = np.load(OUT / f"sweep_{name}.npz")
+        feats = torch.from_numpy(z["feats"]).requires_grad_(True)
+        grids = torch.from_numpy(z["grids"])
+        B, CAM, C = feats.shape[:3]
+        if kind == "std":
+            mod = SphericalSweepStdMasked(CAM, C, 3).eval()
+            vol = mod.sweep(feats, grids, torch.from_numpy(z["grid_masks"]), torch.from_numpy(z["masks"]))
+        else:
+            mod = SphericalSweep(CAM, CAM * C, 3).eval()
+            vol = mod.sweep(feats, grids, None)
+        assert np.array_equal(vol.detach().numpy(), z["vol"])
+        gv = gen.standard_normal(tuple(vol.shape)).astype(np.float32)
+        vol.backward(torch.from_numpy(gv))
+        save(f"sweep_{name}_bwd", grad_vol=gv, grad_feats=feats.grad.numpy())
+    for name in ("sa_d16_s2", "sa_d8_s0", "sa_d8_s2_nopre", "sa_d5_s3"):
+        z = np.load(OUT / f"softargmin_{name}.npz")
+        costs = torch.from_numpy(z["costs"]).requires_grad_(True)
+        reg = DistanceRegressorWithFixedCandidates(96, z["dist"].tolist(), float(z["scale"]), bool(z["pre_interp"])).eval()
+        inv, nc = reg(costs)
+        g_inv = gen.standard_normal(tuple(inv.shape)).astype(np.float32)
+        g_nc = gen.standard_normal(tuple(nc.shape)).astype(np.float32)
+        (g_both,) = torch.autograd.grad([inv, nc], costs, [torch.from_numpy(g_inv), torch.from_numpy(g_nc)],
+                                        retain_graph=True)
+        (g_only_inv,) = torch.autograd.grad(inv, costs, torch.from_numpy(g_inv))
+        save(f"softargmin_{name}_bwd", g_inv=g_inv, g_nc=g_nc, grad_costs=g_both.numpy(),
+             grad_costs_inv_only=g_only_inv.numpy())
+
+
 def main():
+    if "--only-backward" in sys.argv:
+        case_backward()
+        return
     gen = np.random.default_rng(20261017)
     case_grid_sample(gen)
     case_sweeps(gen)
     case_softargmin(gen)
     case_geometry()
+    case_backward()
 
 
 if __name__ == "__main__":

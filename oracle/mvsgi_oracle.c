@@ -247,6 +247,146 @@ void orc_softargmin(const float* costs, int64_t sb, int64_t sd, int64_t sy, int6
 }
 
 /* ------------------------------------------------------------------------- */
+/* Backward passes: what torch.autograd derives from the  */
+/* reference's forward code when training_step differentiates through it       */
+/* (dsta_mvs/model/mvs_model/spherical_sweep_stereo.py:170-202).  Restated op   */
+/* by op from the forward graph; sums run in a fixed order here, whereas        */
+/* autograd's scatter (index_add of torch.gather's backward) and the CUDA       */
+/* kernel's atomics do not, so parity is 1e-5 * max|ref|, not bit-exact.        */
+
+/* adjoint of orc_sample1 for one tap set: adds g * w to the four taps that lie inside the image; taps in the
+ * zero padding receive their share too in autograd, but F.pad's backward drops it (backports.py:58). */
+static inline void orc_scatter1(float* gim, int H, int W, int64_t sy, int64_t sx, const orc_taps* t, float g) {
+  if (t->y0c >= 1 && t->y0c <= H && t->x0c >= 1 && t->x0c <= W) gim[(t->y0c - 1) * sy + (t->x0c - 1) * sx] += g * t->wa;
+  if (t->y1c >= 1 && t->y1c <= H && t->x0c >= 1 && t->x0c <= W) gim[(t->y1c - 1) * sy + (t->x0c - 1) * sx] += g * t->wb;
+  if (t->y0c >= 1 && t->y0c <= H && t->x1c >= 1 && t->x1c <= W) gim[(t->y0c - 1) * sy + (t->x1c - 1) * sx] += g * t->wc;
+  if (t->y1c >= 1 && t->y1c <= H && t->x1c >= 1 && t->x1c <= W) gim[(t->y1c - 1) * sy + (t->x1c - 1) * sx] += g * t->wd;
+}
+
+/* d sum(grad_vol * vol) / d feats for SphericalSweepStdMasked.sweep (spherical_sweep_avg.py:38-136).
+ * grad_vol [B,C,D,Ho,Wo]; grad_feats [B,CAM,C,Hf,Wf] is overwritten. */
+void orc_sweep_std_backward(const float* feats, const float* masks, const float* grids, const uint8_t* grid_masks,
+                            int B, int CAM, int C, int D, int Hf, int Wf, int Hm, int Wm, int Ho, int Wo,
+                            int64_t masks_bstride, int64_t grids_bstride, int64_t gm_bstride, const float* grad_vol,
+                            float* grad_feats) {
+  const int64_t HW = (int64_t)Ho * Wo;
+  memset(grad_feats, 0, sizeof(float) * (size_t)B * CAM * C * Hf * Wf);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b)
+    for (int kc = 0; kc < CAM; ++kc) { /* one thread owns grad_feats[b, kc]: no races */
+      float* f = (float*)malloc(sizeof(float) * (size_t)CAM * C);
+      for (int i = 0; i < D; ++i)
+        for (int64_t px = 0; px < HW; ++px) {
+          int m[MVSGI_MAX_CAMS * 4];
+          orc_taps tk;
+          memset(&tk, 0, sizeof(tk));
+          float summed = 0.0f;
+          for (int cam = 0; cam < CAM; ++cam) {
+            const float* g = grids + b * grids_bstride + (((int64_t)cam * D + i) * HW + px) * 2;
+            orc_taps tf, tm;
+            orc_make_taps(g[0], g[1], Hf, Wf, &tf);
+            if (cam == kc) tk = tf;
+            for (int c = 0; c < C; ++c)
+              f[cam * C + c] = orc_sample1(feats + (((int64_t)b * CAM + cam) * C + c) * Hf * Wf, Hf, Wf, Wf, 1, &tf);
+            orc_make_taps(g[0], g[1], Hm, Wm, &tm);
+            float sm = orc_sample1(masks + b * masks_bstride + (int64_t)cam * Hm * Wm, Hm, Wm, Wm, 1, &tm);
+            int mk = (sm > 0.0f) && (grid_masks[b * gm_bstride + ((int64_t)cam * D + i) * HW + px] != 0);
+            m[cam] = mk;
+            summed += mk ? 1.0f : 0.0f;
+          }
+          if (!(summed > 1.0f) || !m[kc]) continue; /* :125 where(valid, ., 0); :119 where(mask, feat, avg) */
+          float cnt = summed;
+          for (int c = 0; c < C; ++c) {
+            float s = 0.0f;
+            for (int cam = 0; cam < CAM; ++cam) s += f[cam * C + c] * (m[cam] ? 1.0f : 0.0f);
+            float avg = s / cnt;
+            float gv = grad_vol[(((int64_t)b * C + c) * D + i) * HW + px] / cnt; /* :122 (.)/cam_count */
+            /* :122 d/d(f'_j - avg) = 2 (f'_j - avg) gv ; through avg (:114) every camera gets -(sum_j ...)/cnt */
+            float gavg = 0.0f;
+            for (int cam = 0; cam < CAM; ++cam)
+              if (m[cam]) gavg -= 2.0f * (f[cam * C + c] - avg) * gv;
+            float gk = 2.0f * (f[kc * C + c] - avg) * gv + gavg / cnt;
+            orc_scatter1(grad_feats + (((int64_t)b * CAM + kc) * C + c) * Hf * Wf, Hf, Wf, Wf, 1, &tk, gk);
+          }
+        }
+      free(f);
+    }
+}
+
+/* adjoint of SphericalSweep.sweep (spherical_sweep.py:38-68): grad_vol [B,CAM*C,D,Ho,Wo] -> grad_feats */
+void orc_sweep_concat_backward(const float* grids, int B, int CAM, int C, int D, int Hf, int Wf, int Ho, int Wo,
+                               int64_t grids_bstride, const float* grad_vol, float* grad_feats) {
+  const int64_t HW = (int64_t)Ho * Wo;
+  memset(grad_feats, 0, sizeof(float) * (size_t)B * CAM * C * Hf * Wf);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b)
+    for (int cam = 0; cam < CAM; ++cam)
+      for (int i = 0; i < D; ++i)
+        for (int64_t px = 0; px < HW; ++px) {
+          const float* g = grids + b * grids_bstride + (((int64_t)cam * D + i) * HW + px) * 2;
+          orc_taps t;
+          orc_make_taps(g[0], g[1], Hf, Wf, &t);
+          for (int c = 0; c < C; ++c)
+            orc_scatter1(grad_feats + (((int64_t)b * CAM + cam) * C + c) * Hf * Wf, Hf, Wf, Wf, 1, &t,
+                         grad_vol[((((int64_t)b * CAM + cam) * C + c) * D + i) * HW + px]);
+        }
+}
+
+/* Backward of orc_softargmin (distance_regressor.py:51-80): softmax backward (p * (G - sum p G)) followed by the
+ * adjoint of the bilinear upsample.  g_inv [B,1,Ho,Wo] and g_nc [B,D,Ho,Wo] may each be NULL (no gradient through that
+ * output).  grad_costs [B,D,Hin,Win] (channel 0 of the costs tensor) is overwritten. */
+void orc_softargmin_backward(const float* costs, int64_t sb, int64_t sd, int64_t sy, int64_t sx, int B, int D, int Hin,
+                             int Win, int Hout, int Wout, int interp, float scale_h, float scale_w,
+                             const float* inv_dist_idx, const float* g_inv, const float* g_nc, float* grad_costs) {
+  const int64_t HWo = (int64_t)Hout * Wout, HWi = (int64_t)Hin * Win;
+  memset(grad_costs, 0, sizeof(float) * (size_t)B * D * HWi);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < B; ++b) {
+    float* v = (float*)malloc(sizeof(float) * (size_t)D);
+    for (int oy = 0; oy < Hout; ++oy) {
+      int y0 = oy, y1 = oy;
+      float ly0 = 1.0f, ly1 = 0.0f;
+      if (interp) orc_src_index(oy, scale_h, Hin, &y0, &y1, &ly0, &ly1);
+      for (int ox = 0; ox < Wout; ++ox) {
+        int x0 = ox, x1 = ox;
+        float lx0 = 1.0f, lx1 = 0.0f;
+        if (interp) orc_src_index(ox, scale_w, Win, &x0, &x1, &lx0, &lx1);
+        float mx = -INFINITY;
+        for (int d = 0; d < D; ++d) {
+          const float* plane = costs + b * sb + d * sd;
+          v[d] = interp ? orc_upsampled(plane, sy, sx, y0, y1, ly0, ly1, x0, x1, lx0, lx1) : plane[oy * sy + ox * sx];
+          if (v[d] > mx) mx = v[d];
+        }
+        float sum = 0.0f;
+        for (int d = 0; d < D; ++d) { v[d] = expf(v[d] - mx); sum += v[d]; }
+        const int64_t o = (int64_t)oy * Wout + ox;
+        const float gi = g_inv ? g_inv[(int64_t)b * HWo + o] : 0.0f;
+        float dot = 0.0f;
+        for (int d = 0; d < D; ++d) {
+          v[d] = v[d] / sum;
+          float G = gi * inv_dist_idx[d] + (g_nc ? g_nc[((int64_t)b * D + d) * HWo + o] : 0.0f);
+          dot += v[d] * G;
+        }
+        for (int d = 0; d < D; ++d) {
+          float G = gi * inv_dist_idx[d] + (g_nc ? g_nc[((int64_t)b * D + d) * HWo + o] : 0.0f);
+          float gv = v[d] * (G - dot);
+          float* gp = grad_costs + ((int64_t)b * D + d) * HWi;
+          if (interp) {
+            gp[(int64_t)y0 * Win + x0] += ly0 * lx0 * gv;
+            gp[(int64_t)y0 * Win + x1] += ly0 * lx1 * gv;
+            gp[(int64_t)y1 * Win + x0] += ly1 * lx0 * gv;
+            gp[(int64_t)y1 * Win + x1] += ly1 * lx1 * gv;
+          } else {
+            gp[(int64_t)oy * Win + ox] += gv;
+          }
+        }
+      }
+    }
+    free(v);
+  }
+}
+
+/* ------------------------------------------------------------------------- */
 /* Grid precompute the fused kernel absorbs.           */
 /* A.1 Equirectangular.pixel_2_ray  dsta_mvs/mvs_utils/camera_models.py:680-720 */
 static inline void orc_cv_ray(const MvsgiRig* rig, int h, int w, float ray[3]) {

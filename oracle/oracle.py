@@ -114,6 +114,53 @@ def softargmin(costs, inv_dist_idx, interp_scale_factor=0.0, pre_interp=False):
     return inv, nc, am
 
 
+def sweep_std_backward(feats, grids, grid_masks, masks, grad_vol):
+    """d sum(grad_vol * sweep_std(feats, ...)) / d feats  (autograd of spherical_sweep_avg.py:38-136)."""
+    feats, grids, masks, grad_vol = _f32(feats), _f32(grids), _f32(masks), _f32(grad_vol)
+    gm = np.ascontiguousarray(np.asarray(grid_masks).reshape(grids.shape[:5]), dtype=np.uint8)
+    B, CAM, Cc, Hf, Wf = feats.shape
+    _, _, D, Ho, Wo, _ = grids.shape
+    Hm, Wm = masks.shape[-2:]
+    assert grad_vol.shape == (B, Cc, D, Ho, Wo)
+    gf = np.empty_like(feats)
+    lib().orc_sweep_std_backward(
+        _p(feats), _p(masks), _p(grids), _p(gm), B, CAM, Cc, D, Hf, Wf, Hm, Wm, Ho, Wo,
+        C.c_int64(_bstride(masks, CAM * Hm * Wm)), C.c_int64(_bstride(grids, CAM * D * Ho * Wo * 2)),
+        C.c_int64(_bstride(gm, CAM * D * Ho * Wo)), _p(grad_vol), _p(gf))
+    return gf
+
+
+def sweep_concat_backward(feats_shape, grids, grad_vol):
+    """adjoint of sweep_concat (spherical_sweep.py:38-68): grad_vol [B,CAM*C,D,Ho,Wo] -> grad_feats [B,CAM,C,Hf,Wf]."""
+    grids, grad_vol = _f32(grids), _f32(grad_vol)
+    B, CAM, Cc, Hf, Wf = feats_shape
+    _, _, D, Ho, Wo, _ = grids.shape
+    assert grad_vol.shape == (B, CAM * Cc, D, Ho, Wo)
+    gf = np.empty(feats_shape, np.float32)
+    lib().orc_sweep_concat_backward(_p(grids), B, CAM, Cc, D, Hf, Wf, Ho, Wo,
+                                    C.c_int64(_bstride(grids, CAM * D * Ho * Wo * 2)), _p(grad_vol), _p(gf))
+    return gf
+
+
+def softargmin_backward(costs, inv_dist_idx, interp_scale_factor, pre_interp, g_inv=None, g_nc=None):
+    """Backward of softargmin wrt costs[:, 0] -> grad [B,1,D,H,W]."""
+    costs = _f32(costs)
+    B, _, D, H, W = costs.shape
+    c0 = costs[:, 0]
+    idx = _f32(np.asarray(inv_dist_idx).reshape(-1))
+    interp = bool(pre_interp and interp_scale_factor > 0)
+    Ho, Wo = (interp_out_size(H, interp_scale_factor), interp_out_size(W, interp_scale_factor)) if interp else (H, W)
+    scale = np.float32(1.0 / interp_scale_factor) if interp else np.float32(1.0)
+    g_inv = None if g_inv is None else _f32(g_inv)
+    g_nc = None if g_nc is None else _f32(g_nc)
+    out = np.empty((B, D, H, W), np.float32)
+    es = c0.strides
+    lib().orc_softargmin_backward(_p(c0), C.c_int64(es[0] // 4), C.c_int64(es[1] // 4), C.c_int64(es[2] // 4),
+                                  C.c_int64(es[3] // 4), B, D, H, W, Ho, Wo, int(interp), C.c_float(scale),
+                                  C.c_float(scale), _p(idx), _p(g_inv), _p(g_nc), _p(out))
+    return out[:, None]
+
+
 def make_grids(rig_struct: abi.MvsgiRig):
     """create_grids_from_rays (multi_view_camera_model_dataset.py:530-557) in fp32 reference op order."""
     CAM, D, Ho, Wo = rig_struct.num_cams, rig_struct.num_cands, rig_struct.cv_height, rig_struct.cv_width

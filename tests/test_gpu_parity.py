@@ -301,10 +301,17 @@ def test_errors_are_loud(dev):
     with pytest.raises(RuntimeError, match="shape"):
         bad.sweep(torch.zeros(1, 5, 16, 8, 8, device=dev), torch.zeros(1, 5, 2, 4, 4, 2, device=dev),
                   torch.ones(1, 5, 2, 4, 4, 1, dtype=torch.bool, device=dev), torch.ones(1, 5, 1, 8, 8, device=dev))
-    with pytest.raises(NotImplementedError):
-        m.sweep(torch.zeros(1, 3, 16, 8, 8, device=dev, requires_grad=True),
-                torch.zeros(1, 3, 2, 4, 4, 2, device=dev),
-                torch.ones(1, 3, 2, 4, 4, 1, dtype=torch.bool, device=dev), torch.ones(1, 3, 1, 8, 8, device=dev))
+    # training path: gradients flow to feats (row f1); a wrong-shaped upstream gradient is an error, not a guess
+    f = torch.zeros(1, 3, 16, 8, 8, device=dev, requires_grad=True)
+    vol = m.sweep(f, torch.zeros(1, 3, 2, 4, 4, 2, device=dev),
+                  torch.ones(1, 3, 2, 4, 4, 1, dtype=torch.bool, device=dev), torch.ones(1, 3, 1, 8, 8, device=dev))
+    assert vol.requires_grad
+    from mvs_gi_b200 import abi, ops
+    with pytest.raises(RuntimeError, match="grad_vol"):
+        ops.sweep_backward_op(torch.zeros(1, 16, 3, 4, 4, device=dev), f.detach(),
+                              torch.zeros(1, 3, 2, 4, 4, 2, device=dev),
+                              torch.ones(1, 3, 2, 4, 4, 1, dtype=torch.bool, device=dev),
+                              torch.ones(1, 3, 1, 8, 8, device=dev), None, abi.AGG_STD, 4, 4, 2)
 
 
 # ------------------------------------------------------------------ 3. full-size properties (BASELINE.json shapes)
@@ -370,3 +377,139 @@ def test_full_size_softargmin_properties(dev):
     assert torch.equal(nc.argmax(1).cpu(), up.argmax(1))
     ref_inv = (torch.softmax(up, 1) * reg.inv_dist_idx.cpu()).sum(1, keepdim=True)
     assert (inv.cpu() - ref_inv).abs().max().item() <= TOL * ref_inv.abs().max().item()
+
+
+# ------------------------------------------------------------------ 4. backward
+# fp32 atomics accumulate in a non-deterministic order, so gradients are held to 1e-5 * max|ref| (not bit-exact);
+# "exactly zero where nothing samples" IS exact.
+@pytest.mark.parametrize("name", ["std3", "std4"])
+def test_golden_sweep_std_backward(golden, dev, name):
+    from mvs_gi_b200 import modules
+
+    g, gb = golden(f"sweep_{name}"), golden(f"sweep_{name}_bwd")
+    B, CAM, C = g["feats"].shape[:3]
+    m = modules.SphericalSweepStdMasked(CAM, C, 3).to(dev).eval()
+    feats = t(g["feats"], dev).requires_grad_(True)
+    vol = m.sweep(feats, t(g["grids"], dev), t(g["grid_masks"], dev), t(g["masks"], dev))
+    vol.backward(t(gb["grad_vol"], dev))
+    gf, ref = feats.grad.cpu().numpy(), gb["grad_feats"]
+    assert np.array_equal(gf == 0, ref == 0)
+    assert relmax(gf, ref) <= TOL
+
+
+def test_golden_sweep_concat_backward(golden, dev):
+    from mvs_gi_b200 import modules
+
+    g, gb = golden("sweep_concat3"), golden("sweep_concat3_bwd")
+    B, CAM, C = g["feats"].shape[:3]
+    m = modules.SphericalSweep(CAM, CAM * C, 3).to(dev).eval()
+    feats = t(g["feats"], dev).requires_grad_(True)
+    m.sweep(feats, t(g["grids"], dev), None).backward(t(gb["grad_vol"], dev))
+    assert relmax(feats.grad.cpu().numpy(), gb["grad_feats"]) <= TOL
+
+
+@pytest.mark.parametrize("name", ["sa_d16_s2", "sa_d8_s0", "sa_d8_s2_nopre", "sa_d5_s3"])
+def test_golden_softargmin_backward(golden, dev, name):
+    from mvs_gi_b200 import modules
+
+    g, gb = golden(f"softargmin_{name}"), golden(f"softargmin_{name}_bwd")
+    reg = modules.DistanceRegressorWithFixedCandidates(96, list(g["dist"]), float(g["scale"]),
+                                                       bool(g["pre_interp"])).to(dev)
+    costs = t(g["costs"], dev).requires_grad_(True)
+    inv, nc = reg(costs)
+    (both,) = torch.autograd.grad([inv, nc], costs, [t(gb["g_inv"], dev), t(gb["g_nc"], dev)], retain_graph=True)
+    (only,) = torch.autograd.grad(inv, costs, t(gb["g_inv"], dev))
+    assert relmax(both.cpu().numpy(), gb["grad_costs"]) <= TOL
+    assert relmax(only.cpu().numpy(), gb["grad_costs_inv_only"]) <= TOL
+
+
+@pytest.mark.parametrize("name,kw,layout", [
+    ("G16V", dict(feat_hw=(32, 128), mask_hw=(128, 512), cv_hw=(20, 80), n_cands=16), "nchw"),
+    ("4CAM", dict(feat_hw=(32, 128), mask_hw=(128, 512), cv_hw=(20, 80), n_cands=16), "nhwc"),
+    ("G16VV_C48", dict(feat_hw=(16, 64), mask_hw=(64, 256), cv_hw=(10, 40), n_cands=6), "nchw"),
+    ("G16V", dict(feat_hw=(17, 70), mask_hw=(40, 130), cv_hw=(9, 37), n_cands=3), "nchw"),
+])
+def test_sweep_backward_vs_oracle_fused_projection(dev, name, kw, layout):
+    """In-kernel projection + per-frame masks; the oracle consumes the kernel's own grids (as in the forward tests)."""
+    from mvs_gi_b200 import modules, ops
+    from oracle import oracle as orc
+
+    B = 2
+    w, feats, _, masks = _case(name, B, 23, **kw)
+    rig = w.rig()
+    m = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval().attach_rig(rig)
+    f = t(feats, dev)
+    if layout == "nhwc":
+        f = f.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    f.requires_grad_(True)
+    vol = m.sweep(f, None, None, t(masks, dev))
+    gv = np.random.default_rng(5).standard_normal(tuple(vol.shape)).astype(np.float32)
+    vol.backward(t(gv, dev))
+    grids, gm = ops.project_only(rig.to_struct(), dev)
+    ref = orc.sweep_std_backward(feats, grids.cpu().numpy()[None], gm.cpu().numpy()[None], masks, gv)
+    gf = f.grad.cpu().numpy()
+    assert np.array_equal(gf == 0, ref == 0)
+    assert relmax(gf, ref) <= TOL
+
+
+def test_sweep_backward_properties_full_size(dev):
+    """G16V at full size (B=2): Euler identity for the degree-2 std volume, and linearity of the backward in grad_vol."""
+    from mvs_gi_b200 import modules, synthetic
+
+    w = synthetic.WORKLOADS["G16V"]
+    rig = w.rig()
+    B = 2
+    feats = torch.randn((B, w.num_cams, w.feat_chs, *w.feat_hw), device=dev, requires_grad=True)
+    masks = torch.from_numpy(synthetic.fisheye_footprint_masks(w)).to(dev)[None]
+    m = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval().attach_rig(rig)
+    vol = m.sweep(feats, None, None, masks)
+    g1, g2 = torch.randn_like(vol), torch.randn_like(vol)
+    (a,) = torch.autograd.grad(vol, feats, g1, retain_graph=True)
+    (b,) = torch.autograd.grad(vol, feats, g2, retain_graph=True)
+    (c,) = torch.autograd.grad(vol, feats, g1 + 2 * g2)
+    assert float((c - (a + 2 * b)).abs().max()) <= 1e-4 * float(c.abs().max())
+    lhs = float((feats.detach().double() * a.double()).sum())
+    rhs = 2.0 * float((vol.detach().double() * g1.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * abs(rhs)
+
+
+def test_concat_backward_adjoint_full_size(dev):
+    """G8 concat at full size: <sweep(f), g> == <f, sweep^T(g)> (the concat sweep is linear)."""
+    from mvs_gi_b200 import modules, synthetic
+
+    w = synthetic.WORKLOADS["G8"]
+    rig = w.rig()
+    feats = torch.randn((2, w.num_cams, w.feat_chs, *w.feat_hw), device=dev, requires_grad=True)
+    m = modules.SphericalSweep(w.num_cams, w.num_cams * w.feat_chs, 3).to(dev).eval().attach_rig(rig)
+    vol = m.sweep(feats, None)
+    g = torch.randn_like(vol)
+    (gf,) = torch.autograd.grad(vol, feats, g)
+    lhs = float((vol.detach().double() * g.double()).sum())
+    rhs = float((feats.detach().double() * gf.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+
+
+def test_softargmin_backward_vs_oracle_and_torch(dev):
+    """D=16 x2 at a ragged size vs the oracle, and against torch autograd of the reference formulation on the GPU."""
+    import torch.nn.functional as F
+
+    from mvs_gi_b200 import modules, synthetic
+    from oracle import oracle as orc
+
+    w = synthetic.WORKLOADS["G16V"]
+    reg = modules.DistanceRegressorWithFixedCandidates(w.bf, w.dist_list, 2, True).to(dev)
+    costs_np = (np.random.default_rng(3).standard_normal((2, 2, 16, 13, 37)) * 2).astype(np.float32)  # 2 channels: only [:,0] is used
+    costs = t(costs_np, dev).requires_grad_(True)
+    inv, nc = reg(costs)
+    g_inv, g_nc = torch.randn_like(inv), torch.randn_like(nc)
+    (g,) = torch.autograd.grad([inv, nc], costs, [g_inv, g_nc])
+    assert float(g[:, 1].abs().max()) == 0.0
+    ref = orc.softargmin_backward(costs_np[:, :1], reg.inv_dist_idx.cpu().numpy(), 2, True, g_inv.cpu().numpy(),
+                                  g_nc.cpu().numpy())
+    assert relmax(g[:, :1].cpu().numpy(), ref) <= TOL
+    c2 = t(costs_np, dev).requires_grad_(True)
+    up = F.interpolate(c2[:, 0], scale_factor=2, mode="bilinear")
+    p = F.softmax(up, 1)
+    inv_t = torch.sum(p * reg.inv_dist_idx.expand_as(p), 1, keepdim=True)
+    (gt,) = torch.autograd.grad([inv_t, p], c2, [g_inv, g_nc])
+    assert relmax(g.cpu().numpy(), gt.cpu().numpy()) <= TOL

@@ -120,3 +120,45 @@ def test_torch_port_matches_golden(golden):
     g = golden("softargmin_sa_d16_s2")
     inv, nc = port.soft_argmin(torch.from_numpy(g["costs"]), torch.from_numpy(g["inv_dist_idx"]), 2, True)
     assert np.array_equal(inv.numpy(), g["inv_dist"]) and np.array_equal(nc.numpy(), g["norm_costs"])
+
+
+# ------------------------------------------------------------------ backward
+# Goldens: gradients torch.autograd derives from the reference's own forward code (oracle/gen_golden.py case_backward).
+@pytest.mark.parametrize("name", ["std3", "std4"])
+def test_sweep_std_backward(golden, name):
+    g, gb = golden(f"sweep_{name}"), golden(f"sweep_{name}_bwd")
+    gf = orc.sweep_std_backward(g["feats"], g["grids"], g["grid_masks"], g["masks"], gb["grad_vol"])
+    ref = gb["grad_feats"]
+    assert np.array_equal(gf == 0, ref == 0), "pixels no valid voxel samples get exactly zero gradient"
+    assert rel_max(gf, ref) <= 1e-6
+
+
+def test_sweep_concat_backward(golden):
+    g, gb = golden("sweep_concat3"), golden("sweep_concat3_bwd")
+    gf = orc.sweep_concat_backward(g["feats"].shape, g["grids"], gb["grad_vol"])
+    assert rel_max(gf, gb["grad_feats"]) <= 1e-6
+    # the concat sweep is linear in feats: <sweep(f), g> == <f, sweep^T(g)>
+    lhs = float((orc.sweep_concat(g["feats"], g["grids"]).astype(np.float64) * gb["grad_vol"]).sum())
+    rhs = float((g["feats"].astype(np.float64) * gf).sum())
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+
+
+def test_sweep_std_backward_euler(golden):
+    """vol is homogeneous of degree 2 in feats: <feats, d(sum g*vol)/d feats> == 2 <g, vol>."""
+    g, gb = golden("sweep_std3"), golden("sweep_std3_bwd")
+    gf = orc.sweep_std_backward(g["feats"], g["grids"], g["grid_masks"], g["masks"], gb["grad_vol"])
+    lhs = float((g["feats"].astype(np.float64) * gf).sum())
+    rhs = 2.0 * float((g["vol"].astype(np.float64) * gb["grad_vol"]).sum())
+    assert abs(lhs - rhs) <= 1e-5 * abs(rhs)
+
+
+@pytest.mark.parametrize("name", ["sa_d16_s2", "sa_d8_s0", "sa_d8_s2_nopre", "sa_d5_s3"])
+def test_softargmin_backward(golden, name):
+    g, gb = golden(f"softargmin_{name}"), golden(f"softargmin_{name}_bwd")
+    args = (g["costs"], g["inv_dist_idx"], float(g["scale"]), bool(g["pre_interp"]))
+    both = orc.softargmin_backward(*args, gb["g_inv"], gb["g_nc"])
+    only = orc.softargmin_backward(*args, gb["g_inv"], None)
+    assert rel_max(both, gb["grad_costs"]) <= 2e-6
+    assert rel_max(only, gb["grad_costs_inv_only"]) <= 2e-6
+    # softmax is shift-invariant per pixel: the gradient sums to zero over candidates at every LOW-res pixel
+    assert np.abs(both.sum(2)).max() <= 1e-4 * np.abs(both).max()
