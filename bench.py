@@ -41,6 +41,9 @@ def parse():
                     help="per_frame = reference interface [B,CAM,1,Hm,Wm] float32; shared = static inference masks")
     ap.add_argument("--feats-layout", default="nchw", choices=["nchw", "nhwc"],
                     help="memory layout the feature extractor hands over (reference: NCHW)")
+    ap.add_argument("--vol-layout", default="ncdhw", choices=["ncdhw", "ndhwc"],
+                    help="memory layout of the cost volume: ncdhw = the reference's; ndhwc = channels_last_3d strides "
+                         "(MVSGI_FLAG_VOL_CHANNELS_LAST, what cuDNN's NDHWC Conv3d of post_vol consumes)")
     ap.add_argument("--norm-costs", action="store_true", help="also write norm_costs (training consumers)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -181,7 +184,7 @@ def workload_config(args, w):
                     f"cv {w.cv_hw[0]}x{w.cv_hw[1]}, softargmin x{w.scale}",
         "frames_per_gpu_per_step": args.batch, "global_batch": args.batch * args.gpus,
         "grids": "in-kernel projection (Equirectangular surrogates, fixture rig)",
-        "masks": args.masks, "feats_layout": args.feats_layout, "norm_costs": bool(args.norm_costs),
+        "masks": args.masks, "feats_layout": args.feats_layout, "vol_layout": args.vol_layout, "norm_costs": bool(args.norm_costs),
         "parallelism": f"frame-sharded x{args.gpus}, no collective",
         "cache": "3 rotating input sets, each > 126 MB L2",
     }
@@ -224,7 +227,8 @@ def run_b200(args, w):
         f = torch.randn((B, w.num_cams, w.feat_chs, *w.feat_hw), device=dev, generator=gen)
         if args.feats_layout == "nhwc":
             f = f.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
-        calls.append(ops.SweepCall(f, None, None, masks, rig_blob, agg, w.cv_hw[0], w.cv_hw[1], w.num_cands))
+        calls.append(ops.SweepCall(f, None, None, masks, rig_blob, agg, w.cv_hw[0], w.cv_hw[1], w.num_cands,
+                                   channels_last=args.vol_layout == "ndhwc"))
         costs_sets.append(torch.randn((B, 1, w.num_cands, *w.cv_hw), device=dev, generator=gen))
     reg = modules.DistanceRegressorWithFixedCandidates(w.bf, w.dist_list, w.scale, True).to(dev)
     Ho, Wo, scale = reg._out_size(*w.cv_hw)
@@ -268,6 +272,23 @@ def run_b200(args, w):
     ms_total_max = float(t.item())
     value = world * B * K / (ms_total_max * 1e-3)
 
+    # ---- the sweep kernel alone in the other volume layout (same staged inputs), for the layout comparison
+    other_ms = None
+    if rank == 0:
+        oc = ops.SweepCall(calls[0].keep[0], None, None, masks, rig_blob, agg, w.cv_hw[0], w.cv_hw[1], w.num_cands,
+                           channels_last=args.vol_layout != "ndhwc")
+        oc.run(abi.FLAG_STAGE_ONLY)
+        oe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(6)]
+        for a, b in oe:
+            calls[1].run(abi.FLAG_STAGE_ONLY)  # evict: 400 MB of other staged features through L2
+            a.record()
+            oc.run(abi.FLAG_SWEEP_ONLY)
+            b.record()
+        torch.cuda.synchronize()
+        other_ms = sorted(a.elapsed_time(b) for a, b in oe[1:])[2]
+        del oc
+    barrier()
+
     # ---- end to end through the public module API, host buffers
     e2e = None
     if not args.no_e2e:
@@ -275,6 +296,7 @@ def run_b200(args, w):
         builder = builder_cls(w.num_cams, w.out_chs, 3).to(dev).eval().attach_rig(rig)
         if w.aggregate == "std":
             builder.set_static_masks(base_masks[None])  # inference: masks uploaded once (api/inference_class.py:40-45)
+        builder.set_vol_channels_last(args.vol_layout == "ndhwc")
         reg.return_norm_costs = bool(args.norm_costs)
         h_feats = [torch.randn((B, w.num_cams, w.feat_chs, *w.feat_hw)).pin_memory() for _ in range(2)]
         h_costs = [torch.randn((B, 1, w.num_cands, *w.cv_hw)).pin_memory() for _ in range(2)]
@@ -328,7 +350,9 @@ def run_b200(args, w):
                 "traffic": traffic.get("dram_bytes_per_launch") if isinstance(traffic, dict) else None,
                 "traffic_config": traffic.get("config") if isinstance(traffic, dict) else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": sweep_ms,
-                "write_only_frac": (B * w.vol_bytes() / (sweep_ms * 1e-3) / 1e9) / peak}
+                "write_only_frac": (B * w.vol_bytes() / (sweep_ms * 1e-3) / 1e9) / peak,
+                "other_vol_layout": {"layout": "ncdhw" if args.vol_layout == "ndhwc" else "ndhwc", "kernel_ms": other_ms,
+                                     "frac": (alg_bytes / (other_ms * 1e-3) / 1e9 / peak) if other_ms else None}}
     # whole-step algorithmic bytes incl. the reference-interface float masks and the soft-argmin
     step_bytes = B * (w.vol_bytes() + w.feats_bytes() + w.masks_bytes(args.masks == "shared") +
                       w.softargmin_bytes(args.norm_costs))

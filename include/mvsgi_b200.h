@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MVSGI_ABI_VERSION 5
+#define MVSGI_ABI_VERSION 6
 #define MVSGI_MAX_CAMS 4
 #define MVSGI_MAX_CANDS 64
 #define MVSGI_MAX_PEERS 7 /* extra destinations of a candidate-sharded sweep (8 GPUs of one box) */
@@ -63,6 +63,11 @@ enum { MVSGI_MASK_F32 = 0, MVSGI_MASK_U8 = 1 };
 #define MVSGI_FLAG_FEATS_BF16 1u /* stage features as bf16 (fp32 accumulate); stated-tolerance mode */
 #define MVSGI_FLAG_STAGE_ONLY 2u /* only fill the workspace (channels-last feats, packed masks)          */
 #define MVSGI_FLAG_SWEEP_ONLY 4u /* workspace already holds what STAGE_ONLY produced for these args      */
+/* vol (and every peer_vols[i]) is laid out [B, Dvol, Ho, Wo, Cout] in memory — the torch.channels_last_3d strides of
+ * a [B, Cout, Dvol, Ho, Wo] tensor, what cuDNN's NDHWC Conv3d (post_vol, spherical_sweep_avg.py:30-36,165;
+ * common_modules.py:82-115) consumes without a transpose.  Needs feat_chs % 4 == 0 and 16-byte aligned volumes.
+ * SURVEY.md §8 row f2. */
+#define MVSGI_FLAG_VOL_CHANNELS_LAST 8u
 
 /* ---- calibration ------------------------------------------------------- */
 /* One camera the sweep projects into.  rot/trans are the INVERSE pose

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_CAMS = 4
 MAX_CANDS = 64
 MAX_PEERS = 7
@@ -23,6 +23,7 @@ MASK_F32, MASK_U8 = 0, 1
 FLAG_FEATS_BF16 = 1
 FLAG_STAGE_ONLY = 2
 FLAG_SWEEP_ONLY = 4
+FLAG_VOL_CHANNELS_LAST = 8
 
 LIB_NAME = "libmvsgi_b200.so"
 _PKG_DIR = Path(__file__).resolve().parent

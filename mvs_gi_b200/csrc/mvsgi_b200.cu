@@ -48,7 +48,8 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   if (a->struct_size != sizeof(MvsgiSweepArgs)) return MVSGI_E_VERSION;
   if (a->aggregate != MVSGI_AGG_STD && a->aggregate != MVSGI_AGG_CONCAT) return MVSGI_E_UNSUPPORTED;
   if (a->grid_mode != MVSGI_GRID_SUPPLIED && a->grid_mode != MVSGI_GRID_PROJECT) return MVSGI_E_UNSUPPORTED;
-  if (a->flags & ~(MVSGI_FLAG_FEATS_BF16 | MVSGI_FLAG_STAGE_ONLY | MVSGI_FLAG_SWEEP_ONLY)) return MVSGI_E_UNSUPPORTED;
+  if (a->flags & ~(MVSGI_FLAG_FEATS_BF16 | MVSGI_FLAG_STAGE_ONLY | MVSGI_FLAG_SWEEP_ONLY | MVSGI_FLAG_VOL_CHANNELS_LAST))
+    return MVSGI_E_UNSUPPORTED;
   if ((a->flags & MVSGI_FLAG_STAGE_ONLY) && (a->flags & MVSGI_FLAG_SWEEP_ONLY)) return MVSGI_E_UNSUPPORTED;
   if (a->flags & MVSGI_FLAG_FEATS_BF16) return MVSGI_E_UNSUPPORTED;  // reserved; fp32 staging only for now
   if (a->batch <= 0 || a->feat_chs <= 0 || a->out_h <= 0 || a->out_w <= 0) return MVSGI_E_SHAPE;
@@ -66,6 +67,12 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   const int64_t dvol64 = a->vol_num_cands > 0 ? a->vol_num_cands : a->num_cands;
   if ((int64_t)a->cand_offset + a->num_cands > dvol64) return MVSGI_E_SHAPE;
   if (cout64 * dvol64 * a->out_h * a->out_w >= (1ll << 31)) return MVSGI_E_SHAPE;
+  if (a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) {  // one 16-byte store per lane: 4 whole channels, aligned
+    if (a->feat_chs % 4 != 0) return MVSGI_E_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(a->vol) & 15) != 0) return MVSGI_E_STRIDE;
+    for (int i = 0; i < a->num_peers; ++i)
+      if ((reinterpret_cast<uintptr_t>(a->peer_vols[i]) & 15) != 0) return MVSGI_E_STRIDE;
+  }
   if (a->num_peers > 0) {
     if (a->valid_out != nullptr) return MVSGI_E_UNSUPPORTED;
     for (int i = 0; i < a->num_peers; ++i) {
@@ -175,6 +182,7 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
     }
   }
   kp.vol = a->vol;
+  kp.volChannelsLast = (a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) ? 1 : 0;
   kp.validOut = std_agg ? a->valid_out : nullptr;
   kp.dOff = a->cand_offset;
   kp.Dvol = a->vol_num_cands > 0 ? a->vol_num_cands : a->num_cands;
@@ -182,14 +190,20 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   for (int i = 0; i < a->num_peers; ++i) kp.peerDelta[i] = (long long)((reinterpret_cast<intptr_t>(a->peer_vols[i]) - reinterpret_cast<intptr_t>(a->vol)) / 4);
 }
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS = false>
-cudaError_t launch_sweep(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
-  auto kern = mvsgi::sweep_kernel<CAM, AGG, FULLC, VALID, PEERS>;
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL>
+cudaError_t launch_sweep_cl(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
+  auto kern = mvsgi::sweep_kernel<CAM, AGG, FULLC, VALID, PEERS, CL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, mvsgi::kSweepThreads, smem, st>>>(kp, rig);
   g_launches++;
   return cudaGetLastError();
+}
+
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS = false>
+cudaError_t launch_sweep(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
+  return kp.volChannelsLast ? launch_sweep_cl<CAM, AGG, FULLC, VALID, PEERS, true>(kp, rig, grid, smem, st)
+                            : launch_sweep_cl<CAM, AGG, FULLC, VALID, PEERS, false>(kp, rig, grid, smem, st);
 }
 
 template <int CAM, int AGG>

@@ -59,7 +59,7 @@ struct SweepKP {
   uint8_t* validOut;
   // candidate-sharded sweep: the D candidates of this call are candidates [dOff, dOff + D) of a volume with Dvol
   // candidates; every store is repeated at vol + peerDelta[i] (elements) for i < numPeers (peer-mapped volumes)
-  int dOff, Dvol, numPeers;
+  int dOff, Dvol, numPeers, volChannelsLast;
   long long peerDelta[MVSGI_MAX_PEERS];
 };
 
@@ -110,6 +110,24 @@ MVSGI_DEV uint32_t mask_eval(const MaskWords& m, uint32_t info) {
 MVSGI_DEV void st_stream(float* p, float v) {  // written once, never re-read here: keep it out of L1
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+MVSGI_DEV void st_stream4(float* p, const float* v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3])
+               : "memory");
+}
+// The 4 consecutive channels a lane owns of one voxel.  CL (channels-last volume, MVSGI_FLAG_VOL_CHANNELS_LAST): they
+// are 16 contiguous bytes, so a quad writes the 64 bytes of a 16-channel group and a warp 8 consecutive pixels = 512
+// contiguous bytes.  Otherwise (NCDHW) they are `cs` elements apart and a warp writes one 32-byte sector per channel.
+template <bool CL>
+MVSGI_DEV void st_lane(float* p, const float* v, int nst, long long cs) {
+  if (CL) {
+    if (nst >= 4) st_stream4(p, v);  // host: C % 4 == 0, so a lane owns 4 real channels or none
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nst) st_stream(p + i * cs, v[i]);
+  }
+}
 
 // Tap-table entry of one (camera, candidate, pixel): element offset of tap (y0, x0) inside a staged (b, cam, cg)
 // image, frac x (x - x0) and frac y.  backports.py:41-55 with the zero padding folded into the staged image; samples
@@ -135,7 +153,7 @@ MVSGI_DEV void make_entry(const SweepKP& kp, float gx, float gy, int& off, float
 // The record stride is odd, so the 8 records a warp reads at a time sit in 8 different banks.
 __host__ __device__ constexpr int entry_words(int cam) { return (2 + 3 * cam) | 1; }
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS>
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL>
 __global__ void __launch_bounds__(kSweepThreads, 2)
 sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -273,7 +291,8 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       // Per-frame lane pointers and loop constants, pinned in registers (the empty asm keeps the compiler from
       // re-deriving them from the kernel parameters inside the loop).
       const float* fbq = kp.feat + (long long)b * kp.fsB + cLane;
-      float* vq = kp.vol + ((long long)b * kp.Cout + cLane) * cs;
+      // NCDHW: voxel (c, po) at frame + c*cs + po; channels-last: at frame + po*Cout + c
+      float* vq = kp.vol + (long long)b * kp.Cout * cs + (CL ? (long long)cLane : (long long)cLane * cs);
       int fsY = kp.fsY, zeroOff = kp.zeroOff, csr = cs;
       asm volatile("" : "+l"(fbq), "+l"(vq), "+r"(fsY), "+r"(zeroOff), "+r"(csr));
 
@@ -288,9 +307,9 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         const int n = __popc(v);
         const bool need = act && (AGG == MVSGI_AGG_CONCAT || n > 1);  // spherical_sweep_avg.py:106-111
         const float* fcg = fbq;
-        float* vcg = vq + po;
+        float* vcg = vq + (CL ? (long long)po * kp.Cout : (long long)po);
 
-        for (int cg = 0; cg < kp.CG; ++cg, fcg += kp.fsCg, vcg += kCG * (long long)csr) {
+        for (int cg = 0; cg < kp.CG; ++cg, fcg += kp.fsCg, vcg += (CL ? (long long)kCG : kCG * (long long)csr)) {
           float f[CAM][4];
 #pragma unroll
           for (int cam = 0; cam < CAM; ++cam) {
@@ -303,7 +322,17 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
               const float lxe = ld ? lx : 0.0f;
               const float* t = fcg + off;
               const float* t1 = t + fsY;
+#ifdef MVSGI_EXP_PRED
+              float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta, tc = ta, td = ta;
+              if (ld) {
+                ta = ldg4(t);
+                tc = ldg4(t + kCG);
+                tb = ldg4(t1);
+                td = ldg4(t1 + kCG);
+              }
+#else
               const float4 ta = ldg4(t), tc = ldg4(t + kCG), tb = ldg4(t1), td = ldg4(t1 + kCG);
+#endif
               const float wa = hx * hy, wb = hx * ly, wc = lxe * hy, wd = lxe * ly;  // backports.py:52-55
               // backports.py:86  Ia*wa + Ib*wb + Ic*wc + Id*wd (left to right, contracted into FMAs)
               f[cam][0] = fmaf(td.x, wd, fmaf(tc.x, wc, fmaf(tb.x, wb, ta.x * wa)));
@@ -337,16 +366,9 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
               }
             }
             if (act) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (i < nst) st_stream(vcg + i * (long long)csr, o[i]);
+              st_lane<CL>(vcg, o, nst, csr);
               if (PEERS) {  // the all-gather of the candidate slices, fused: same voxel into every peer's volume
-                for (int pr = 0; pr < kp.numPeers; ++pr) {
-                  float* pv = vcg + kp.peerDelta[pr];
-#pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    if (i < nst) st_stream(pv + i * (long long)csr, o[i]);
-                }
+                for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(vcg + kp.peerDelta[pr], o, nst, csr);
               }
               if (VALID && cg == 0 && q == 0) kp.validOut[(long long)b * cs + po] = (n > 1) ? 1 : 0;
             }
@@ -354,17 +376,10 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
             if (act) {
 #pragma unroll
               for (int cam = 0; cam < CAM; ++cam) {
-                float* dst = vcg + (long long)(cam * kp.C) * csr;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if (i < nst) st_stream(dst + i * (long long)csr, f[cam][i]);
+                float* dst = vcg + (CL ? (long long)(cam * kp.C) : (long long)(cam * kp.C) * csr);
+                st_lane<CL>(dst, f[cam], nst, csr);
                 if (PEERS) {
-                  for (int pr = 0; pr < kp.numPeers; ++pr) {
-                    float* pv = dst + kp.peerDelta[pr];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                      if (i < nst) st_stream(pv + i * (long long)csr, f[cam][i]);
-                  }
+                  for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(dst + kp.peerDelta[pr], f[cam], nst, csr);
                 }
               }
             }

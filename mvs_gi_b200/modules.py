@@ -67,12 +67,22 @@ class _SweepBase(nn.Module):
         self._rig: Optional[Rig] = None
         self._rig_blob: Optional[Tensor] = None
         self._static_masks: Optional[Tensor] = None
+        # Memory layout of the volume the sweep kernel writes.  False = the reference's NCDHW.  True = the same
+        # [B,C,D,Ho,Wo] tensor with torch.channels_last_3d strides: the kernel then stores 512 contiguous bytes per
+        # warp and post_vol's Conv3d runs cuDNN's NDHWC path on it.  Values are identical.
+        self.vol_channels_last = False
 
     # ---- B200-specific configuration (not part of the reference interface) ----
     def attach_rig(self, rig: Optional[Rig]) -> "_SweepBase":
         """Evaluate the sampling grid in-kernel from this calibration instead of reading `grids`."""
         self._rig = rig
         self._rig_blob = ops.rig_to_blob(rig.to_struct()) if rig is not None else None
+        return self
+
+    def set_vol_channels_last(self, on: bool = True) -> "_SweepBase":
+        """Emit the cost volume channels-last (NDHWC in memory) and keep post_vol's weights in the same format."""
+        self.vol_channels_last = bool(on)
+        self.post_vol.to(memory_format=torch.channels_last_3d if on else torch.contiguous_format)
         return self
 
     def set_static_masks(self, masks: Optional[Tensor]) -> "_SweepBase":
@@ -103,7 +113,8 @@ class _SweepBase(nn.Module):
         if self._aggregate == abi.AGG_STD and self._static_masks is not None:
             masks = self._static_masks
         return ops.sweep_op(feats, grids, grid_masks, masks if self._aggregate == abi.AGG_STD else None,
-                            self._rig_blob, self._aggregate, int(Ho), int(Wo), int(D), want_valid)
+                            self._rig_blob, self._aggregate, int(Ho), int(Wo), int(D), want_valid,
+                            self.vol_channels_last)
 
 
 class SphericalSweepStdMasked(_SweepBase):

@@ -52,10 +52,12 @@ class SweepCall:
     def __init__(self, feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor], masks: Optional[Tensor],
                  rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
                  want_valid: bool = False, out: Optional[Tensor] = None, cand_offset: int = 0,
-                 peer_ptrs: Sequence[int] = (), describe_only: bool = False):
+                 peer_ptrs: Sequence[int] = (), describe_only: bool = False, channels_last: bool = False):
         """`out`, `cand_offset`, `peer_ptrs`: candidate-sharded sweep.  `out` is the full [B, Cout, Dvol, Ho, Wo]
         volume (contiguous); this call fills candidates [cand_offset, cand_offset + num_cands) of it and of every
         peer-mapped volume in `peer_ptrs` (raw device pointers from sharding.PeerVolume).
+        `channels_last`: the volume is a [B, Cout, D, Ho, Wo] tensor with torch.channels_last_3d strides (memory
+        [B, D, Ho, Wo, Cout], MVSGI_FLAG_VOL_CHANNELS_LAST) — what post_vol's Conv3d takes without a transpose.
         `describe_only`: fill the argument struct (inputs only) without allocating the volume or the workspace —
         how the backward op describes the forward problem to mvsgi_sweep_backward_f32."""
         self.lib = abi.load_library()
@@ -66,7 +68,8 @@ class SweepCall:
         a = abi.MvsgiSweepArgs()
         a.struct_size = C.sizeof(abi.MvsgiSweepArgs)
         a.aggregate = aggregate
-        a.flags = 0
+        self.base_flags = abi.FLAG_VOL_CHANNELS_LAST if channels_last else 0
+        a.flags = self.base_flags
         a.batch, a.num_cams, a.feat_chs, a.num_cands = B, CAM, Cc, num_cands
         a.feat_h, a.feat_w, a.out_h, a.out_w = Hf, Wf, out_h, out_w
         a.feats = feats.data_ptr()
@@ -138,12 +141,15 @@ class SweepCall:
         if out is None:
             if cand_offset or len(peer_ptrs):
                 raise RuntimeError("a candidate-sharded sweep needs the full volume passed as `out`")
-            self.vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=torch.float32, device=feats.device)
+            self.vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=torch.float32, device=feats.device,
+                                   memory_format=torch.channels_last_3d if channels_last else torch.contiguous_format)
         else:
             _require_cuda(out, "out")
-            if (out.dtype != torch.float32 or out.dim() != 5 or not out.is_contiguous() or out.shape[0] != B
-                    or out.shape[1] != cout or tuple(out.shape[3:]) != (out_h, out_w)):
-                raise RuntimeError(f"`out` must be a contiguous float32 [B, {cout}, Dvol, {out_h}, {out_w}] volume")
+            fmt = torch.channels_last_3d if channels_last else torch.contiguous_format
+            if (out.dtype != torch.float32 or out.dim() != 5 or not out.is_contiguous(memory_format=fmt)
+                    or out.shape[0] != B or out.shape[1] != cout or tuple(out.shape[3:]) != (out_h, out_w)):
+                raise RuntimeError(f"`out` must be a float32 [B, {cout}, Dvol, {out_h}, {out_w}] volume, "
+                                   f"{'channels_last_3d' if channels_last else 'contiguous'}")
             if cand_offset < 0 or cand_offset + num_cands > out.shape[2]:
                 raise RuntimeError("candidate slice does not fit the output volume")
             if len(peer_ptrs) > abi.MAX_PEERS:
@@ -169,21 +175,23 @@ class SweepCall:
         self.args = a
 
     def launch_count(self, flags: int = 0) -> int:
-        self.args.flags = flags
+        self.args.flags = flags | self.base_flags
         n = self.lib.mvsgi_sweep_launch_count(C.byref(self.args))
-        self.args.flags = 0
+        self.args.flags = self.base_flags
         return int(n)
 
     def run(self, flags: int = 0) -> None:
-        self.args.flags = flags
+        self.args.flags = flags | self.base_flags
         with torch.cuda.device(self.device):
             rc = self.lib.mvsgi_sweep_f32(C.byref(self.args), _stream_ptr(self.device))
-        self.args.flags = 0
+        self.args.flags = self.base_flags
         abi.check(rc, "mvsgi_sweep_f32")
 
 
-def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid):
-    call = SweepCall(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid)
+def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
+                channels_last=False):
+    call = SweepCall(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
+                     channels_last=channels_last)
     call.run()
     # inputs and workspace are only read by kernels already enqueued on this stream; the caching allocator reuses
     # freed blocks in stream order, so dropping the references here is safe.
@@ -193,15 +201,17 @@ def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out
 @torch.library.custom_op("mvsgi::sweep", mutates_args=())
 def sweep_op(feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor], masks: Optional[Tensor],
              rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
-             want_valid: bool) -> Tuple[Tensor, Tensor]:
-    return _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid)
+             want_valid: bool, channels_last: bool = False) -> Tuple[Tensor, Tensor]:
+    return _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
+                       channels_last)
 
 
 @sweep_op.register_fake
-def _(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid):
+def _(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid, channels_last=False):
     B, CAM, Cc = feats.shape[:3]
     cout = Cc if aggregate == abi.AGG_STD else CAM * Cc
-    vol = feats.new_empty((B, cout, num_cands, out_h, out_w))
+    vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=feats.dtype, device=feats.device,
+                      memory_format=torch.channels_last_3d if channels_last else torch.contiguous_format)
     valid = feats.new_empty((B, num_cands, out_h, out_w) if (want_valid and aggregate == abi.AGG_STD) else (0,),
                             dtype=torch.uint8)
     return vol, valid
@@ -283,7 +293,7 @@ def _(grad_vol, feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out
 
 
 def _sweep_setup(ctx, inputs, output):
-    feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, _ = inputs
+    feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands = inputs[:9]
     ctx.save_for_backward(feats, grids, grid_masks, masks, rig_blob)
     ctx.meta = (aggregate, out_h, out_w, num_cands)
 
@@ -293,7 +303,7 @@ def _sweep_bwd(ctx, grad_vol, grad_valid):
     gf = None
     if ctx.needs_input_grad[0] and grad_vol is not None:
         gf = sweep_backward_op(grad_vol, feats, grids, grid_masks, masks, rig_blob, *ctx.meta)
-    return gf, None, None, None, None, None, None, None, None, None
+    return gf, None, None, None, None, None, None, None, None, None, None
 
 
 sweep_op.register_autograd(_sweep_bwd, setup_context=_sweep_setup)

@@ -270,6 +270,62 @@ def test_candidate_slices_and_peer_stores_on_one_gpu(dev):
                       cand_offset=1)
 
 
+def test_channels_last_volume_is_the_same_volume(dev):
+    """MVSGI_FLAG_VOL_CHANNELS_LAST: the [B,C,D,Ho,Wo] volume written with channels_last_3d
+    strides holds bit-identical values (std 3/4 cameras incl. C=12 and C=48, concat, candidate slices + peer stores),
+    and post_vol (cuDNN Conv3d + BN + LeakyReLU, spherical_sweep_avg.py:165) gives the reference-layout result."""
+    from mvs_gi_b200 import abi, modules, ops, sharding, synthetic
+    from oracle import oracle as orc
+
+    for name, kw, chs in [("G16V", dict(feat_hw=(24, 96), mask_hw=(96, 384), cv_hw=(12, 72), n_cands=7), None),
+                          ("4CAM", dict(feat_hw=(17, 70), mask_hw=(40, 130), cv_hw=(9, 37), n_cands=3), 12),
+                          ("G16VV_C48", dict(feat_hw=(16, 64), mask_hw=(64, 256), cv_hw=(10, 40), n_cands=6), None)]:
+        w, feats, _, masks = _case(name, 2, 61, **kw)
+        if chs is not None:
+            feats = np.ascontiguousarray(feats[:, :, :chs])
+        C = feats.shape[2]
+        rig = w.rig()
+        f, mk = t(feats, dev), t(masks, dev)
+        m = modules.SphericalSweepStdMasked(w.num_cams, C, 3).to(dev).eval().attach_rig(rig)
+        with torch.no_grad():
+            ref = m.sweep(f, None, None, mk)
+            ref_post = m(f, None, None, mk)
+            m.set_vol_channels_last(True)
+            cl = m.sweep(f, None, None, mk)
+            cl_post = m(f, None, None, mk)
+        assert cl.shape == ref.shape and cl.is_contiguous(memory_format=torch.channels_last_3d)
+        assert cl.stride(1) == 1 and not cl.is_contiguous()
+        assert torch.equal(cl, ref)
+        assert relmax(cl_post.cpu().numpy(), ref_post.cpu().numpy()) <= 1e-4  # cuDNN picks another algorithm
+        # candidate slices + a stand-in peer volume, channels-last
+        vol = torch.full_like(cl, float("nan"))
+        peer = torch.full_like(cl, float("nan"))
+        assert vol.is_contiguous(memory_format=torch.channels_last_3d)
+        for r in range(2):
+            d0, d1 = sharding.balanced_range(w.num_cands, r, 2)
+            blob = ops.rig_to_blob(sharding.sub_rig(rig, d0, d1).to_struct())
+            ops.SweepCall(f, None, None, mk, blob, abi.AGG_STD, *w.cv_hw, d1 - d0, out=vol, cand_offset=d0,
+                          peer_ptrs=[peer.data_ptr()], channels_last=True).run()
+        assert torch.equal(vol, ref) and torch.equal(peer, ref)
+        with pytest.raises(RuntimeError, match="channels_last_3d"):
+            ops.SweepCall(f, None, None, mk, ops.rig_to_blob(rig.to_struct()), abi.AGG_STD, *w.cv_hw, w.num_cands,
+                          out=torch.empty_like(ref), channels_last=True)
+    # concat
+    w = synthetic.small(synthetic.WORKLOADS["G8"], feat_hw=(16, 64), cv_hw=(10, 40))
+    feats = synthetic.make_feats(w, 2, 62)
+    g0, _ = orc.make_grids(w.rig().to_struct())
+    cat = modules.SphericalSweep(w.num_cams, w.out_chs, 3).to(dev).eval()
+    with torch.no_grad():
+        ref = cat.sweep(t(feats, dev), t(g0[None], dev), None)
+        cl = cat.set_vol_channels_last(True).sweep(t(feats, dev), t(g0[None], dev), None)
+    assert cl.stride(1) == 1 and torch.equal(cl, ref)
+    # channels not a multiple of 4 cannot be stored as 16-byte vectors: loud error, no fallback
+    w, feats, _, masks = _case("G16V", 1, 63, feat_hw=(16, 64), mask_hw=(64, 256), cv_hw=(10, 40), n_cands=2)
+    m = modules.SphericalSweepStdMasked(w.num_cams, 6, 3).to(dev).eval().attach_rig(w.rig()).set_vol_channels_last()
+    with pytest.raises(RuntimeError, match="shape"):
+        m.sweep(t(np.ascontiguousarray(feats[:, :, :6]), dev), None, None, t(masks, dev))
+
+
 def test_candidate_sharded_sweep_two_gpus(dev):
     """NCCL all-gather variant and the fused peer-store variant on 2 GPUs of one box (skipped on a 1-GPU box)."""
     import json
