@@ -8,6 +8,7 @@
 #include "softargmin.cuh"
 #include "stage.cuh"
 #include "sweep.cuh"
+#include "sweep_walk.cuh"
 #include "backward.cuh"
 
 namespace {
@@ -32,6 +33,8 @@ struct SweepPlan {
   int dch, num_chunks, num_runs, run_len, num_items, max_pairs, grid, group_px, interleave;
   size_t smem_bytes;
   int cout;
+  bool walk;              // channels-last volume: sweep_walk.cuh
+  int w_len, w_segs, w_num_seg;
 };
 
 int mask_pitch_words(int mask_w) { return (mask_w + 31) / 32 + 2; }  // zero guard word + data words + zero guard
@@ -144,6 +147,34 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   p->group_px = env_int("MVSGI_GROUP_PX", p->interleave ? 8 : 32);
   if (p->group_px < 1) p->group_px = 1;
   p->smem_bytes = align_up((int64_t)p->max_pairs * per_pair + (int64_t)p->run_len * 12 + 16, 16);
+  p->walk = false;
+
+  // Channels-last volume, experiment (MVSGI_WALK=1, off by default because it measures slower, see sweep_walk.cuh):
+  // walking quads.  One 512-thread CTA per SM; a run is w_segs segments of
+  // w_len consecutive pixels taken round-robin over the image; task = (segment, candidate), one per quad when
+  // w_segs * dch == 128.
+  if ((a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) && env_int("MVSGI_WALK", 0)) {
+    const int sms = device_sms();
+    const int nquads = mvsgi::kWalkThreads / 4;
+    int segs = env_int("MVSGI_WALK_SEGS", nquads / dch);
+    if (segs < 1) segs = 1;
+    const int64_t wbudget = env_int("MVSGI_WALK_TABLE_BYTES", 200 * 1024);
+    int64_t len = ((int64_t)P + (int64_t)sms * segs - 1) / ((int64_t)sms * segs);
+    const int64_t len_cap = wbudget / ((int64_t)segs * ((int64_t)dch * per_pair + 12));
+    if (len > len_cap) len = len_cap;
+    if (len >= 1) {
+      p->walk = true;
+      p->w_len = (int)len;
+      p->w_segs = segs;
+      p->w_num_seg = (int)((P + len - 1) / len);
+      p->num_runs = (p->w_num_seg + segs - 1) / segs;
+      p->run_len = segs * (int)len;
+      p->num_items = p->num_runs * p->num_chunks;
+      p->max_pairs = segs * dch * (int)len;
+      p->grid = p->num_items < sms ? p->num_items : sms;
+      p->smem_bytes = align_up((int64_t)p->max_pairs * per_pair + (int64_t)p->run_len * 12 + 16, 16);
+    }
+  }
   return MVSGI_OK;
 }
 
@@ -156,6 +187,7 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   kp.Ho = a->out_h; kp.Wo = a->out_w; kp.Hf = a->feat_h; kp.Wf = a->feat_w; kp.Hm = a->mask_h; kp.Wm = a->mask_w;
   kp.P = a->out_h * a->out_w; kp.numRuns = p.num_runs; kp.runLen = p.run_len; kp.dch = p.dch;
   kp.numChunks = p.num_chunks; kp.numItems = p.num_items; kp.maxPairs = p.max_pairs; kp.grpPx = p.group_px; kp.interleave = p.interleave;
+  kp.wL = p.walk ? p.w_len : 0; kp.wSegs = p.walk ? p.w_segs : 0; kp.wNumSeg = p.walk ? p.w_num_seg : 0;
   kp.feat = ws_feats;
   kp.fsY = Wp * mvsgi::kCG;
   kp.fsCg = Hp1 * kp.fsY;
@@ -220,9 +252,34 @@ cudaError_t dispatch_flags(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int gr
                : launch_sweep<CAM, AGG, false, false>(kp, rig, grid, smem, st);
 }
 
+template <int CAM, int AGG, bool VALID, bool PEERS>
+cudaError_t launch_walk(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
+  auto kern = mvsgi::sweep_walk_kernel<CAM, AGG, VALID, PEERS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, mvsgi::kWalkThreads, smem, st>>>(kp, rig);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+template <int CAM, int AGG>
+cudaError_t dispatch_walk(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
+  if (kp.numPeers > 0) return launch_walk<CAM, AGG, false, true>(kp, rig, grid, smem, st);
+  if (AGG == MVSGI_AGG_STD && kp.validOut != nullptr) return launch_walk<CAM, AGG, true, false>(kp, rig, grid, smem, st);
+  return launch_walk<CAM, AGG, false, false>(kp, rig, grid, smem, st);
+}
+
 template <int AGG>
 cudaError_t dispatch_cams(int cams, const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
                           cudaStream_t st) {
+  if (kp.wL > 0) {
+    switch (cams) {
+      case 1: return dispatch_walk<1, AGG>(kp, rig, grid, smem, st);
+      case 2: return dispatch_walk<2, AGG>(kp, rig, grid, smem, st);
+      case 3: return dispatch_walk<3, AGG>(kp, rig, grid, smem, st);
+      default: return dispatch_walk<4, AGG>(kp, rig, grid, smem, st);
+    }
+  }
   switch (cams) {
     case 1: return dispatch_flags<1, AGG>(kp, rig, grid, smem, st);
     case 2: return dispatch_flags<2, AGG>(kp, rig, grid, smem, st);

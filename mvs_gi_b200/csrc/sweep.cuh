@@ -41,6 +41,7 @@ struct SweepKP {
   int B, C, D, Cout, CG;
   int Ho, Wo, Hf, Wf, Hm, Wm;
   int P, numRuns, runLen, dch, numChunks, numItems, maxPairs, grpPx, interleave;
+  int wL, wSegs, wNumSeg;  // sweep_walk.cuh: segment length, segments per run, segments in the image
   // staged features: element (b, cam, cg, yp, xp, c) at feat[b*fsB + cam*fsCam + cg*fsCg + yp*fsY + xp*16 + c]
   const float* feat;
   long long fsB;
@@ -322,23 +323,15 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
               const float lxe = ld ? lx : 0.0f;
               const float* t = fcg + off;
               const float* t1 = t + fsY;
-#ifdef MVSGI_EXP_PRED
-              float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta, tc = ta, td = ta;
-              if (ld) {
-                ta = ldg4(t);
-                tc = ldg4(t + kCG);
-                tb = ldg4(t1);
-                td = ldg4(t1 + kCG);
-              }
-#else
               const float4 ta = ldg4(t), tc = ldg4(t + kCG), tb = ldg4(t1), td = ldg4(t1 + kCG);
-#endif
-              const float wa = hx * hy, wb = hx * ly, wc = lxe * hy, wd = lxe * ly;  // backports.py:52-55
-              // backports.py:86  Ia*wa + Ib*wb + Ic*wc + Id*wd (left to right, contracted into FMAs)
-              f[cam][0] = fmaf(td.x, wd, fmaf(tc.x, wc, fmaf(tb.x, wb, ta.x * wa)));
-              f[cam][1] = fmaf(td.y, wd, fmaf(tc.y, wc, fmaf(tb.y, wb, ta.y * wa)));
-              f[cam][2] = fmaf(td.z, wd, fmaf(tc.z, wc, fmaf(tb.z, wb, ta.z * wa)));
-              f[cam][3] = fmaf(td.w, wd, fmaf(tc.w, wc, fmaf(tb.w, wb, ta.w * wa)));
+              const float wa = __fmul_rn(hx, hy), wb = __fmul_rn(hx, ly), wc = __fmul_rn(lxe, hy),
+                          wd = __fmul_rn(lxe, ly);  // backports.py:52-55
+              // backports.py:86  Ia*wa + Ib*wb + Ic*wc + Id*wd, summed as (column x0) + (column x1) — the same
+              // bits as sweep_walk.cuh, which keeps the two columns of a patch in registers
+              f[cam][0] = __fadd_rn(fmaf(tb.x, wb, __fmul_rn(ta.x, wa)), fmaf(td.x, wd, __fmul_rn(tc.x, wc)));
+              f[cam][1] = __fadd_rn(fmaf(tb.y, wb, __fmul_rn(ta.y, wa)), fmaf(td.y, wd, __fmul_rn(tc.y, wc)));
+              f[cam][2] = __fadd_rn(fmaf(tb.z, wb, __fmul_rn(ta.z, wa)), fmaf(td.z, wd, __fmul_rn(tc.z, wc)));
+              f[cam][3] = __fadd_rn(fmaf(tb.w, wb, __fmul_rn(ta.w, wa)), fmaf(td.w, wd, __fmul_rn(tc.w, wc)));
             } else {
               f[cam][0] = f[cam][1] = f[cam][2] = f[cam][3] = 0.0f;
             }

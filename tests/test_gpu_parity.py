@@ -326,6 +326,41 @@ def test_channels_last_volume_is_the_same_volume(dev):
         m.sweep(t(np.ascontiguousarray(feats[:, :, :6]), dev), None, None, t(masks, dev))
 
 
+def test_walking_quads_experiment_is_bit_identical(dev, monkeypatch):
+    """sweep_walk.cuh (MVSGI_WALK=1, not the default: it measures slower) must still be the same function:
+    bit-identical to the default kernel for std / concat, 3 and 4 cameras, C=48, ragged sizes, per-frame masks."""
+    from mvs_gi_b200 import modules, synthetic
+    from oracle import oracle as orc
+
+    for name, kw in [("G16V", dict(feat_hw=(24, 96), mask_hw=(96, 384), cv_hw=(12, 72), n_cands=7)),
+                     ("4CAM", dict(feat_hw=(17, 70), mask_hw=(40, 130), cv_hw=(9, 37), n_cands=3)),
+                     ("G16VV_C48", dict(feat_hw=(16, 64), mask_hw=(64, 256), cv_hw=(10, 40), n_cands=16))]:
+        w, feats, _, masks = _case(name, 3, 71, **kw)
+        m = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval().attach_rig(w.rig())
+        m.set_vol_channels_last(True)
+        with torch.no_grad():
+            monkeypatch.setenv("MVSGI_WALK", "0")
+            ref, ref_valid = m.sweep_with_valid(t(feats, dev), None, None, t(masks, dev))
+            monkeypatch.setenv("MVSGI_WALK", "1")
+            for segs in ("", "3", "32"):
+                monkeypatch.setenv("MVSGI_WALK_SEGS", segs)
+                got, got_valid = m.sweep_with_valid(t(feats, dev), None, None, t(masks, dev))
+                assert torch.equal(got, ref) and torch.equal(got_valid, ref_valid), (name, segs)
+    monkeypatch.setenv("MVSGI_WALK_SEGS", "")
+    w = synthetic.small(synthetic.WORKLOADS["G8"], feat_hw=(16, 64), cv_hw=(10, 40))
+    feats = synthetic.make_feats(w, 2, 72)
+    g0, _ = orc.make_grids(w.rig().to_struct())
+    grids = np.repeat(g0[None], 2, 0)
+    grids[1] += 0.01  # per-frame grids: the table is rebuilt per frame
+    cat = modules.SphericalSweep(w.num_cams, w.out_chs, 3).to(dev).eval().set_vol_channels_last(True)
+    with torch.no_grad():
+        monkeypatch.setenv("MVSGI_WALK", "0")
+        ref = cat.sweep(t(feats, dev), t(grids, dev), None)
+        monkeypatch.setenv("MVSGI_WALK", "1")
+        got = cat.sweep(t(feats, dev), t(grids, dev), None)
+    assert torch.equal(got, ref)
+
+
 def test_candidate_sharded_sweep_two_gpus(dev):
     """NCCL all-gather variant and the fused peer-store variant on 2 GPUs of one box (skipped on a 1-GPU box)."""
     import json
