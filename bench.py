@@ -41,11 +41,12 @@ def parse():
                     help="per_frame = reference interface [B,CAM,1,Hm,Wm] float32; shared = static inference masks")
     ap.add_argument("--feats-layout", default="nchw", choices=["nchw", "nhwc"],
                     help="memory layout the feature extractor hands over (reference: NCHW)")
-    ap.add_argument("--vol-layout", default="ncdhw", choices=["ncdhw", "ndhwc"],
+    ap.add_argument("--vol-layout", default="ndhwc", choices=["ncdhw", "ndhwc"],
                     help="memory layout of the cost volume: ncdhw = the reference's; ndhwc = channels_last_3d strides "
                          "(MVSGI_FLAG_VOL_CHANNELS_LAST, what cuDNN's NDHWC Conv3d of post_vol consumes)")
     ap.add_argument("--norm-costs", action="store_true", help="also write norm_costs (training consumers)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the other-layout / bf16-staging kernel timings")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-frames", type=int, default=1, help="frames per step of the CPU reference arm")
     return ap.parse_args()
@@ -272,21 +273,31 @@ def run_b200(args, w):
     ms_total_max = float(t.item())
     value = world * B * K / (ms_total_max * 1e-3)
 
-    # ---- the sweep kernel alone in the other volume layout (same staged inputs), for the layout comparison
-    other_ms = None
-    if rank == 0:
+    # ---- the sweep kernel alone in the other volume layout, and with bf16-staged features (stated-tolerance mode),
+    # on the same inputs; each timed launch follows a staging pass over another 400 MB input set (L2 evicted)
+    def time_variant(channels_last, feats_bf16):
         oc = ops.SweepCall(calls[0].keep[0], None, None, masks, rig_blob, agg, w.cv_hw[0], w.cv_hw[1], w.num_cands,
-                           channels_last=args.vol_layout != "ndhwc")
-        oc.run(abi.FLAG_STAGE_ONLY)
-        oe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(6)]
-        for a, b in oe:
-            calls[1].run(abi.FLAG_STAGE_ONLY)  # evict: 400 MB of other staged features through L2
-            a.record()
+                           channels_last=channels_last, feats_bf16=feats_bf16)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(6)]
+        for e in ev:
+            calls[1].run(abi.FLAG_STAGE_ONLY)
+            e[0].record()
+            oc.run(abi.FLAG_STAGE_ONLY)
+            e[1].record()
             oc.run(abi.FLAG_SWEEP_ONLY)
-            b.record()
+            e[2].record()
         torch.cuda.synchronize()
-        other_ms = sorted(a.elapsed_time(b) for a, b in oe[1:])[2]
-        del oc
+        med = lambda v: sorted(v)[len(v) // 2]
+        return med([e[0].elapsed_time(e[1]) for e in ev[1:]]), med([e[1].elapsed_time(e[2]) for e in ev[1:]])
+
+    variants = None
+    if rank == 0 and not args.no_variants:
+        cl = args.vol_layout == "ndhwc"
+        _, other_ms = time_variant(not cl, False)
+        bf_stage_ms, bf_ms = time_variant(cl, True)
+        variants = {"other_vol_layout": {"layout": "ncdhw" if cl else "ndhwc", "kernel_ms": other_ms},
+                    "feats_bf16": {"layout": args.vol_layout, "kernel_ms": bf_ms, "stage_ms": bf_stage_ms,
+                                   "tolerance": "max|vol - fp32 vol| <= 1e-2 * max|vol| (tests/test_gpu_parity.py)"}}
     barrier()
 
     # ---- end to end through the public module API, host buffers
@@ -350,9 +361,11 @@ def run_b200(args, w):
                 "traffic": traffic.get("dram_bytes_per_launch") if isinstance(traffic, dict) else None,
                 "traffic_config": traffic.get("config") if isinstance(traffic, dict) else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": sweep_ms,
-                "write_only_frac": (B * w.vol_bytes() / (sweep_ms * 1e-3) / 1e9) / peak,
-                "other_vol_layout": {"layout": "ncdhw" if args.vol_layout == "ndhwc" else "ndhwc", "kernel_ms": other_ms,
-                                     "frac": (alg_bytes / (other_ms * 1e-3) / 1e9 / peak) if other_ms else None}}
+                "write_only_frac": (B * w.vol_bytes() / (sweep_ms * 1e-3) / 1e9) / peak}
+    if variants:
+        for v in variants.values():
+            v["frac"] = alg_bytes / (v["kernel_ms"] * 1e-3) / 1e9 / peak
+        roofline["variants"] = variants
     # whole-step algorithmic bytes incl. the reference-interface float masks and the soft-argmin
     step_bytes = B * (w.vol_bytes() + w.feats_bytes() + w.masks_bytes(args.masks == "shared") +
                       w.softargmin_bytes(args.norm_costs))

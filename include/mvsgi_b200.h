@@ -60,7 +60,10 @@ enum {
 /* Element type of the masks tensor. */
 enum { MVSGI_MASK_F32 = 0, MVSGI_MASK_U8 = 1 };
 /* flags for MvsgiSweepArgs.flags */
-#define MVSGI_FLAG_FEATS_BF16 1u /* stage features as bf16 (fp32 accumulate); stated-tolerance mode */
+/* Stage the features as bfloat16 (round to nearest even; taps widened back to fp32, all arithmetic in fp32): halves
+ * the bytes every tap moves through L1/L2.  Stated-tolerance mode: max|vol - fp32 vol| <= 1e-2 * max|vol|, validity
+ * mask unchanged (SURVEY.md §8c criterion 4).  Not available with valid_out or peer_vols; the backward ignores it. */
+#define MVSGI_FLAG_FEATS_BF16 1u
 #define MVSGI_FLAG_STAGE_ONLY 2u /* only fill the workspace (channels-last feats, packed masks)          */
 #define MVSGI_FLAG_SWEEP_ONLY 4u /* workspace already holds what STAGE_ONLY produced for these args      */
 /* vol (and every peer_vols[i]) is laid out [B, Dvol, Ho, Wo, Cout] in memory — the torch.channels_last_3d strides of

@@ -54,7 +54,8 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   if (a->flags & ~(MVSGI_FLAG_FEATS_BF16 | MVSGI_FLAG_STAGE_ONLY | MVSGI_FLAG_SWEEP_ONLY | MVSGI_FLAG_VOL_CHANNELS_LAST))
     return MVSGI_E_UNSUPPORTED;
   if ((a->flags & MVSGI_FLAG_STAGE_ONLY) && (a->flags & MVSGI_FLAG_SWEEP_ONLY)) return MVSGI_E_UNSUPPORTED;
-  if (a->flags & MVSGI_FLAG_FEATS_BF16) return MVSGI_E_UNSUPPORTED;  // reserved; fp32 staging only for now
+  // bf16 staging is a plain-forward mode: no validity output, no peer stores
+  if ((a->flags & MVSGI_FLAG_FEATS_BF16) && (a->valid_out != nullptr || a->num_peers > 0)) return MVSGI_E_UNSUPPORTED;
   if (a->batch <= 0 || a->feat_chs <= 0 || a->out_h <= 0 || a->out_w <= 0) return MVSGI_E_SHAPE;
   if (a->num_cams < 1 || a->num_cams > MVSGI_MAX_CAMS) return MVSGI_E_SHAPE;
   if (a->num_cands < 1) return MVSGI_E_SHAPE;
@@ -114,7 +115,8 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   p->n_mask_images = std_agg ? (p->per_frame_masks ? a->batch : 1) * a->num_cams : 0;
   p->mask_pitch = std_agg ? mask_pitch_words(a->mask_w) : 0;
   p->mask_words = std_agg ? (a->mask_h + 2) * p->mask_pitch : 0;
-  p->feats_bytes = align_up((int64_t)a->batch * a->num_cams * p->cg * (a->feat_h + 3) * (a->feat_w + 2) * mvsgi::kCG * 4, 256);
+  p->feats_bytes = align_up((int64_t)a->batch * a->num_cams * p->cg * (a->feat_h + 3) * (a->feat_w + 2) * mvsgi::kCG *
+                                ((a->flags & MVSGI_FLAG_FEATS_BF16) ? 2 : 4), 256);
   p->mask_bytes = align_up((int64_t)p->n_mask_images * p->mask_words * 4 + 16, 256);  // +16: funnel-shift over-read
   p->flag_bytes = 256;
   p->total_bytes = p->feats_bytes + p->mask_bytes + p->flag_bytes;
@@ -153,7 +155,8 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   // walking quads.  One 512-thread CTA per SM; a run is w_segs segments of
   // w_len consecutive pixels taken round-robin over the image; task = (segment, candidate), one per quad when
   // w_segs * dch == 128.
-  if ((a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) && env_int("MVSGI_WALK", 0)) {
+  if ((a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) && !(a->flags & MVSGI_FLAG_FEATS_BF16) && a->num_cams >= 3 &&
+      env_int("MVSGI_WALK", 0)) {
     const int sms = device_sms();
     const int nquads = mvsgi::kWalkThreads / 4;
     int segs = env_int("MVSGI_WALK_SEGS", nquads / dch);
@@ -215,6 +218,7 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   }
   kp.vol = a->vol;
   kp.volChannelsLast = (a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) ? 1 : 0;
+  kp.featsBf16 = (a->flags & MVSGI_FLAG_FEATS_BF16) ? 1 : 0;
   kp.validOut = std_agg ? a->valid_out : nullptr;
   kp.dOff = a->cand_offset;
   kp.Dvol = a->vol_num_cands > 0 ? a->vol_num_cands : a->num_cands;
@@ -222,9 +226,9 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   for (int i = 0; i < a->num_peers; ++i) kp.peerDelta[i] = (long long)((reinterpret_cast<intptr_t>(a->peer_vols[i]) - reinterpret_cast<intptr_t>(a->vol)) / 4);
 }
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL>
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16 = false>
 cudaError_t launch_sweep_cl(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
-  auto kern = mvsgi::sweep_kernel<CAM, AGG, FULLC, VALID, PEERS, CL>;
+  auto kern = mvsgi::sweep_kernel<CAM, AGG, FULLC, VALID, PEERS, CL, BF16>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, mvsgi::kSweepThreads, smem, st>>>(kp, rig);
@@ -242,6 +246,13 @@ template <int CAM, int AGG>
 cudaError_t dispatch_flags(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
   const bool fullc = kp.C % mvsgi::kCG == 0;
   const bool valid = kp.validOut != nullptr;
+  if (kp.featsBf16) {  // validate_and_plan: no validity output, no peers in this mode
+    if (kp.volChannelsLast)
+      return fullc ? launch_sweep_cl<CAM, AGG, true, false, false, true, true>(kp, rig, grid, smem, st)
+                   : launch_sweep_cl<CAM, AGG, false, false, false, true, true>(kp, rig, grid, smem, st);
+    return fullc ? launch_sweep_cl<CAM, AGG, true, false, false, false, true>(kp, rig, grid, smem, st)
+                 : launch_sweep_cl<CAM, AGG, false, false, false, false, true>(kp, rig, grid, smem, st);
+  }
   if (kp.numPeers > 0)
     return fullc ? launch_sweep<CAM, AGG, true, false, true>(kp, rig, grid, smem, st)
                  : launch_sweep<CAM, AGG, false, false, true>(kp, rig, grid, smem, st);
@@ -274,8 +285,6 @@ cudaError_t dispatch_cams(int cams, const mvsgi::SweepKP& kp, const MvsgiRig& ri
                           cudaStream_t st) {
   if (kp.wL > 0) {
     switch (cams) {
-      case 1: return dispatch_walk<1, AGG>(kp, rig, grid, smem, st);
-      case 2: return dispatch_walk<2, AGG>(kp, rig, grid, smem, st);
       case 3: return dispatch_walk<3, AGG>(kp, rig, grid, smem, st);
       default: return dispatch_walk<4, AGG>(kp, rig, grid, smem, st);
     }
@@ -431,10 +440,16 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
     if ((int64_t)N * p.cg * x_blocks >= (1ll << 31) || Hp1 > 65535) return MVSGI_E_SHAPE;
     dim3 grid((unsigned)(N * p.cg * x_blocks), Hp1);
     const int chan_fastest = (a->feats_stride[2] == 1 && a->feats_stride[4] != 1) ? 1 : 0;
-    mvsgi::stage_feats_kernel<<<grid, 256, 0, st>>>(a->feats, a->feats_stride[0], a->num_cams, a->feats_stride[1],
-                                                    a->feats_stride[2], a->feats_stride[3], a->feats_stride[4],
-                                                    a->feat_chs, p.cg, a->feat_h, a->feat_w, x_blocks, chan_fastest,
-                                                    ws_feats);
+    if (a->flags & MVSGI_FLAG_FEATS_BF16)
+      mvsgi::stage_feats_kernel<true><<<grid, 256, 0, st>>>(a->feats, a->feats_stride[0], a->num_cams,
+                                                            a->feats_stride[1], a->feats_stride[2], a->feats_stride[3],
+                                                            a->feats_stride[4], a->feat_chs, p.cg, a->feat_h,
+                                                            a->feat_w, x_blocks, chan_fastest, ws_feats);
+    else
+      mvsgi::stage_feats_kernel<false><<<grid, 256, 0, st>>>(a->feats, a->feats_stride[0], a->num_cams,
+                                                             a->feats_stride[1], a->feats_stride[2], a->feats_stride[3],
+                                                             a->feats_stride[4], a->feat_chs, p.cg, a->feat_h,
+                                                             a->feat_w, x_blocks, chan_fastest, ws_feats);
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

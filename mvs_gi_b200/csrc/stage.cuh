@@ -7,6 +7,7 @@
 //   pack_masks_kernel  : masks [.., Hm, Wm] (float32 0/1 or u8/bool) -> zero-framed bit images, bit set iff mask > 0
 //                        (the "bilinear(mask) > 0" test of spherical_sweep_avg.py:92-96 only needs those bits).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -15,10 +16,13 @@ namespace mvsgi {
 constexpr int kStagePx = 544;     // padded pixels per block (one block covers a whole 514-pixel padded row)
 constexpr int kStagePitch = 546;  // smem row pitch in floats (== 2 mod 8: conflict-free both ways)
 
+// BF16 (MVSGI_FLAG_FEATS_BF16): the staged image holds bfloat16 (round to nearest even), 32 bytes per pixel; the
+// sweep converts back to fp32 and accumulates in fp32 (stated-tolerance mode, SURVEY.md §8c criterion 4).
+template <bool BF16>
 __global__ void __launch_bounds__(256)
 stage_feats_kernel(const float* __restrict__ src, long long sN0, int n1, long long sN1, long long sC, long long sH,
                    long long sW, int C, int CG, int Hf, int Wf, int xBlocks, int chanFastest,
-                   float* __restrict__ dst) {
+                   float* __restrict__ dst_) {
   __shared__ float tile[16 * kStagePitch];
   const int Wp = Wf + 2, Hp1 = Hf + 3;
   const int xb = blockIdx.x % xBlocks;
@@ -27,11 +31,16 @@ stage_feats_kernel(const float* __restrict__ src, long long sN0, int n1, long lo
   const int yp = blockIdx.y;
   const int xp0 = xb * kStagePx;
   const int t = threadIdx.x;
-  float4* drow = reinterpret_cast<float4*>(dst + (((long long)ncg * Hp1 + yp) * Wp + xp0) * 16);
+  const long long rowOff = (((long long)ncg * Hp1 + yp) * Wp + xp0) * 16;  // elements
+  float4* drow = reinterpret_cast<float4*>(dst_ + rowOff);
+  uint2* drow16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dst_) + rowOff);
   const int npx = min(kStagePx, Wp - xp0);
 
   if ((yp == 0) || (yp > Hf)) {  // zero frame rows
-    for (int idx = t; idx < npx * 4; idx += 256) drow[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int idx = t; idx < npx * 4; idx += 256) {
+      if (BF16) drow16[idx] = make_uint2(0u, 0u);
+      else drow[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     return;
   }
   const float* s = src + (long long)(n / n1) * sN0 + (long long)(n % n1) * sN1 + (long long)(yp - 1) * sH;
@@ -68,7 +77,15 @@ stage_feats_kernel(const float* __restrict__ src, long long sN0, int n1, long lo
     v.y = tile[(c4 * 4 + 1) * kStagePitch + px];
     v.z = tile[(c4 * 4 + 2) * kStagePitch + px];
     v.w = tile[(c4 * 4 + 3) * kStagePitch + px];
-    drow[idx] = v;
+    if (BF16) {
+      const uint32_t lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.x)) |
+                          ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.y)) << 16);
+      const uint32_t hi = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.z)) |
+                          ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.w)) << 16);
+      drow16[idx] = make_uint2(lo, hi);
+    } else {
+      drow[idx] = v;
+    }
   }
 }
 

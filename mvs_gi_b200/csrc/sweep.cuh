@@ -60,11 +60,19 @@ struct SweepKP {
   uint8_t* validOut;
   // candidate-sharded sweep: the D candidates of this call are candidates [dOff, dOff + D) of a volume with Dvol
   // candidates; every store is repeated at vol + peerDelta[i] (elements) for i < numPeers (peer-mapped volumes)
-  int dOff, Dvol, numPeers, volChannelsLast;
+  int dOff, Dvol, numPeers, volChannelsLast, featsBf16;
   long long peerDelta[MVSGI_MAX_PEERS];
 };
 
 MVSGI_DEV float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// bf16-staged features (MVSGI_FLAG_FEATS_BF16): 4 channels = 8 bytes, widened to fp32 exactly (bf16 is the top half)
+MVSGI_DEV float4 ldg4(const uint16_t* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xFFFF0000u));
+}
+template <bool BF16> struct StagedT { typedef float type; };
+template <> struct StagedT<true> { typedef uint16_t type; };
 
 // Mask test of spherical_sweep_avg.py:92-96 for 0/1 (non-negative) masks: bilinear(mask) > 0  <=>  some tap has
 // weight > 0 and a set mask bit.  Encodes the padded bit position of tap (y0, x0) and which of the other three taps
@@ -154,7 +162,7 @@ MVSGI_DEV void make_entry(const SweepKP& kp, float gx, float gy, int& off, float
 // The record stride is odd, so the 8 records a warp reads at a time sit in 8 different banks.
 __host__ __device__ constexpr int entry_words(int cam) { return (2 + 3 * cam) | 1; }
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL>
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16>
 __global__ void __launch_bounds__(kSweepThreads, 2)
 sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -291,7 +299,8 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       if (AGG == MVSGI_AGG_STD && kp.perFrameMasks && !kp.perFrameGrids && b + 1 < kp.B) lookup_masks(b + 1);
       // Per-frame lane pointers and loop constants, pinned in registers (the empty asm keeps the compiler from
       // re-deriving them from the kernel parameters inside the loop).
-      const float* fbq = kp.feat + (long long)b * kp.fsB + cLane;
+      typedef typename StagedT<BF16>::type FT;  // element type of the staged features (same element offsets)
+      const FT* fbq = reinterpret_cast<const FT*>(kp.feat) + (long long)b * kp.fsB + cLane;
       // NCDHW: voxel (c, po) at frame + c*cs + po; channels-last: at frame + po*Cout + c
       float* vq = kp.vol + (long long)b * kp.Cout * cs + (CL ? (long long)cLane : (long long)cLane * cs);
       int fsY = kp.fsY, zeroOff = kp.zeroOff, csr = cs;
@@ -307,7 +316,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         const uint32_t v = (rec[1] >> vsh) & 0xFFu;
         const int n = __popc(v);
         const bool need = act && (AGG == MVSGI_AGG_CONCAT || n > 1);  // spherical_sweep_avg.py:106-111
-        const float* fcg = fbq;
+        const FT* fcg = fbq;
         float* vcg = vq + (CL ? (long long)po * kp.Cout : (long long)po);
 
         for (int cg = 0; cg < kp.CG; ++cg, fcg += kp.fsCg, vcg += (CL ? (long long)kCG : kCG * (long long)csr)) {
@@ -321,8 +330,8 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
               const float lx = __uint_as_float(rec[3 + 3 * cam]), ly = __uint_as_float(rec[4 + 3 * cam]);
               const float hx = ld ? 1.0f - lx : 0.0f, hy = 1.0f - ly;
               const float lxe = ld ? lx : 0.0f;
-              const float* t = fcg + off;
-              const float* t1 = t + fsY;
+              const FT* t = fcg + off;
+              const FT* t1 = t + fsY;
               const float4 ta = ldg4(t), tc = ldg4(t + kCG), tb = ldg4(t1), td = ldg4(t1 + kCG);
               const float wa = __fmul_rn(hx, hy), wb = __fmul_rn(hx, ly), wc = __fmul_rn(lxe, hy),
                           wd = __fmul_rn(lxe, ly);  // backports.py:52-55

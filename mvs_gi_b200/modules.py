@@ -71,6 +71,8 @@ class _SweepBase(nn.Module):
         # [B,C,D,Ho,Wo] tensor with torch.channels_last_3d strides: the kernel then stores 512 contiguous bytes per
         # warp and post_vol's Conv3d runs cuDNN's NDHWC path on it.  Values are identical.
         self.vol_channels_last = False
+        # Stage the features as bfloat16 inside the sweep (fp32 arithmetic): stated-tolerance mode, 1e-2 * max|vol|.
+        self.feats_bf16 = False
 
     # ---- B200-specific configuration (not part of the reference interface) ----
     def attach_rig(self, rig: Optional[Rig]) -> "_SweepBase":
@@ -83,6 +85,13 @@ class _SweepBase(nn.Module):
         """Emit the cost volume channels-last (NDHWC in memory) and keep post_vol's weights in the same format."""
         self.vol_channels_last = bool(on)
         self.post_vol.to(memory_format=torch.channels_last_3d if on else torch.contiguous_format)
+        return self
+
+    def set_feats_bf16(self, on: bool = True) -> "_SweepBase":
+        """Stated-tolerance mode (SURVEY.md §8c criterion 4): taps read bfloat16-rounded features, half the L1/L2
+        bytes; masks / validity are unchanged, |vol - fp32 vol| <= 1e-2 * max|vol|.  Forward only (no validity output);
+        the backward differentiates the fp32 formulation (straight-through)."""
+        self.feats_bf16 = bool(on)
         return self
 
     def set_static_masks(self, masks: Optional[Tensor]) -> "_SweepBase":
@@ -114,7 +123,7 @@ class _SweepBase(nn.Module):
             masks = self._static_masks
         return ops.sweep_op(feats, grids, grid_masks, masks if self._aggregate == abi.AGG_STD else None,
                             self._rig_blob, self._aggregate, int(Ho), int(Wo), int(D), want_valid,
-                            self.vol_channels_last)
+                            self.vol_channels_last, self.feats_bf16)
 
 
 class SphericalSweepStdMasked(_SweepBase):

@@ -52,12 +52,14 @@ class SweepCall:
     def __init__(self, feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor], masks: Optional[Tensor],
                  rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
                  want_valid: bool = False, out: Optional[Tensor] = None, cand_offset: int = 0,
-                 peer_ptrs: Sequence[int] = (), describe_only: bool = False, channels_last: bool = False):
+                 peer_ptrs: Sequence[int] = (), describe_only: bool = False, channels_last: bool = False,
+                 feats_bf16: bool = False):
         """`out`, `cand_offset`, `peer_ptrs`: candidate-sharded sweep.  `out` is the full [B, Cout, Dvol, Ho, Wo]
         volume (contiguous); this call fills candidates [cand_offset, cand_offset + num_cands) of it and of every
         peer-mapped volume in `peer_ptrs` (raw device pointers from sharding.PeerVolume).
         `channels_last`: the volume is a [B, Cout, D, Ho, Wo] tensor with torch.channels_last_3d strides (memory
         [B, D, Ho, Wo, Cout], MVSGI_FLAG_VOL_CHANNELS_LAST) — what post_vol's Conv3d takes without a transpose.
+        `feats_bf16`: stage the features as bfloat16 (MVSGI_FLAG_FEATS_BF16, stated-tolerance mode, fp32 arithmetic).
         `describe_only`: fill the argument struct (inputs only) without allocating the volume or the workspace —
         how the backward op describes the forward problem to mvsgi_sweep_backward_f32."""
         self.lib = abi.load_library()
@@ -68,7 +70,8 @@ class SweepCall:
         a = abi.MvsgiSweepArgs()
         a.struct_size = C.sizeof(abi.MvsgiSweepArgs)
         a.aggregate = aggregate
-        self.base_flags = abi.FLAG_VOL_CHANNELS_LAST if channels_last else 0
+        self.base_flags = (abi.FLAG_VOL_CHANNELS_LAST if channels_last else 0) | \
+                          (abi.FLAG_FEATS_BF16 if feats_bf16 else 0)
         a.flags = self.base_flags
         a.batch, a.num_cams, a.feat_chs, a.num_cands = B, CAM, Cc, num_cands
         a.feat_h, a.feat_w, a.out_h, a.out_w = Hf, Wf, out_h, out_w
@@ -189,9 +192,9 @@ class SweepCall:
 
 
 def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                channels_last=False):
+                channels_last=False, feats_bf16=False):
     call = SweepCall(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                     channels_last=channels_last)
+                     channels_last=channels_last, feats_bf16=feats_bf16)
     call.run()
     # inputs and workspace are only read by kernels already enqueued on this stream; the caching allocator reuses
     # freed blocks in stream order, so dropping the references here is safe.
@@ -201,13 +204,14 @@ def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out
 @torch.library.custom_op("mvsgi::sweep", mutates_args=())
 def sweep_op(feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor], masks: Optional[Tensor],
              rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
-             want_valid: bool, channels_last: bool = False) -> Tuple[Tensor, Tensor]:
+             want_valid: bool, channels_last: bool = False, feats_bf16: bool = False) -> Tuple[Tensor, Tensor]:
     return _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                       channels_last)
+                       channels_last, feats_bf16)
 
 
 @sweep_op.register_fake
-def _(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid, channels_last=False):
+def _(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid, channels_last=False,
+      feats_bf16=False):
     B, CAM, Cc = feats.shape[:3]
     cout = Cc if aggregate == abi.AGG_STD else CAM * Cc
     vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=feats.dtype, device=feats.device,
@@ -303,7 +307,7 @@ def _sweep_bwd(ctx, grad_vol, grad_valid):
     gf = None
     if ctx.needs_input_grad[0] and grad_vol is not None:
         gf = sweep_backward_op(grad_vol, feats, grids, grid_masks, masks, rig_blob, *ctx.meta)
-    return gf, None, None, None, None, None, None, None, None, None, None
+    return gf, None, None, None, None, None, None, None, None, None, None, None
 
 
 sweep_op.register_autograd(_sweep_bwd, setup_context=_sweep_setup)

@@ -176,3 +176,11 @@ def make_grids_f64(rig_struct: abi.MvsgiRig):
     gm = np.empty((CAM, D, Ho, Wo), np.uint8)
     lib().orc_make_grids_f64(C.byref(rig_struct), _p(grids), _p(gm))
     return grids, gm.astype(bool)
+
+
+def bf16_round(a: np.ndarray) -> np.ndarray:
+    """float32 -> nearest bfloat16 (ties to even) -> float32: what MVSGI_FLAG_FEATS_BF16 stores in the staged image
+    (test infrastructure for the stated-tolerance mode, SURVEY.md §8c criterion 4)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    r = ((u >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
+    return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)

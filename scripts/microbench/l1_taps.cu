@@ -39,6 +39,9 @@ __global__ void __launch_bounds__(512) k(const float* __restrict__ buf, float* o
   else if (MODE == 3) base = lane * 8;
   else if (MODE == 4) base = ((int)(1.6f * (lane >> 3))) * 16 + (lane & 7) * 4;
   else if (MODE == 7) base = ((int)(1.6f * (lane >> 1))) * 16 + (lane & 1) * 8;
+  else if (MODE == 10) base = quad * 8 + q * 2;         // bf16-staged: quad = 32 B of px k (stride 1 px), LDG.64
+  else if (MODE == 11) base = quad * 16 + q * 4;        // fp32, stride 1 px (the measured G16V step), LDG.128
+  else if (MODE == 12) base = (quad * 3) * 8 + q * 2;   // bf16-staged, stride 3 px (no two quads share a sector)
   else if (MODE == 8) base = (((int)(1.6f * quad)) & ~1) * 16 + q * 8;  // LDG.256, quad = one ALIGNED 128-B line
   else if (MODE == 9) base = (((int)(1.6f * quad)) & ~1) * 16 + q * 8;  // mode 8 + LDG.128 from the next line for odd quads
   else base = ((int)(1.6f * (quad & 3))) * 16 + q * 4 + (quad >> 2) * 514 * 16;
@@ -56,6 +59,8 @@ __global__ void __launch_bounds__(512) k(const float* __restrict__ buf, float* o
       if (MODE == 9) { idx &= ~7; F8 r = ldg256(buf + idx); acc += (r.v[0] + r.v[1]) + (r.v[2] + r.v[3]) + (r.v[4] + r.v[5]) + (r.v[6] + r.v[7]);
         if (quad & 1) { float4 r2 = ldg128(buf + idx + 32); acc += (r2.x + r2.y) + (r2.z + r2.w); } }
       else if (MODE == 1 || MODE == 3 || MODE == 7 || MODE == 8) { idx &= ~7; F8 r = ldg256(buf + idx); acc += (r.v[0] + r.v[1]) + (r.v[2] + r.v[3]) + (r.v[4] + r.v[5]) + (r.v[6] + r.v[7]); }
+      else if (MODE == 10 || MODE == 12) { idx = (base + o * 0 + ((warp * 37 + it * 13) * 8) + u * 8 * 29) % (WIN - 64); idx &= ~1;
+        float2 r = __ldg(reinterpret_cast<const float2*>(buf + idx)); acc += r.x + r.y; }
       else if (MODE == 5) { float4 r = *reinterpret_cast<const float4*>(sm + idx); acc += (r.x + r.y) + (r.z + r.w); }
       else { float4 r = ldg128(buf + idx); acc += (r.x + r.y) + (r.z + r.w); }
     }
@@ -98,5 +103,8 @@ int main() {
   run<7>("LDG.256, 2 lanes/px (16px x 64B, stride 1.6px)", 32, buf, out, cyc, blocks);
   run<8>("LDG.256 aligned pair line per quad (8 lines, 1024B)", 32, buf, out, cyc, blocks);
   run<9>("mode 8 + LDG.128 next line for odd quads (1024B useful+256)", 32, buf, out, cyc, blocks);
+  run<11>("LDG.128 sparse (quad=64B, stride 1px)", 16, buf, out, cyc, blocks);
+  run<10>("LDG.64 bf16 chunk (quad=32B, stride 1px)", 8, buf, out, cyc, blocks);
+  run<12>("LDG.64 bf16 chunk (quad=32B, stride 3px)", 8, buf, out, cyc, blocks);
   return 0;
 }

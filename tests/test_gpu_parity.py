@@ -361,6 +361,47 @@ def test_walking_quads_experiment_is_bit_identical(dev, monkeypatch):
     assert torch.equal(got, ref)
 
 
+def test_bf16_staged_features_stated_tolerance(dev):
+    """MVSGI_FLAG_FEATS_BF16 (SURVEY.md §8c criterion 4): the kernel must equal the fp32 oracle run on
+    bfloat16-rounded features to 1e-5 (same arithmetic, rounded inputs), keep the validity mask / zero pattern
+    bit-exact, and stay within 1e-2 * max|ref| of the un-rounded fp32 volume.  Both volume layouts, std and concat."""
+    from mvs_gi_b200 import modules, ops, synthetic
+    from oracle import oracle as orc
+
+    BF16_TOL = 1e-2
+    for name, kw in [("G16V", dict(feat_hw=(32, 128), mask_hw=(128, 512), cv_hw=(20, 80), n_cands=16)),
+                     ("4CAM", dict(feat_hw=(17, 70), mask_hw=(40, 130), cv_hw=(9, 37), n_cands=3)),
+                     ("G16VV_C48", dict(feat_hw=(16, 64), mask_hw=(64, 256), cv_hw=(10, 40), n_cands=6))]:
+        w, feats, _, masks = _case(name, 2, 81, **kw)
+        rig = w.rig()
+        m = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval().attach_rig(rig)
+        with torch.no_grad():
+            full = m.sweep(t(feats, dev), None, None, t(masks, dev))
+            m.set_feats_bf16(True)
+            got = m.sweep(t(feats, dev), None, None, t(masks, dev))
+            got_cl = m.set_vol_channels_last(True).sweep(t(feats, dev), None, None, t(masks, dev))
+            grids, gm = ops.project_only(rig.to_struct(), dev)
+        assert torch.equal(got, got_cl)
+        g, gmn = grids.cpu().numpy()[None], gm.cpu().numpy()[None]
+        ref_rounded = orc.sweep_std(orc.bf16_round(feats), g, gmn, masks)
+        ref = orc.sweep_std(feats, g, gmn, masks)
+        v = got.cpu().numpy()
+        assert np.array_equal(v == 0, ref == 0), "validity / zero pattern must not depend on the staging dtype"
+        assert relmax(v, ref_rounded) <= TOL
+        assert relmax(v, ref) <= BF16_TOL
+        assert relmax(v, full.cpu().numpy()) <= BF16_TOL and not torch.equal(got, full)
+        with pytest.raises(RuntimeError, match="unsupported"):
+            m.sweep_with_valid(t(feats, dev), None, None, t(masks, dev))
+    w = synthetic.small(synthetic.WORKLOADS["G8"], feat_hw=(16, 64), cv_hw=(10, 40))
+    feats = synthetic.make_feats(w, 2, 82)
+    g0, _ = orc.make_grids(w.rig().to_struct())
+    cat = modules.SphericalSweep(w.num_cams, w.out_chs, 3).to(dev).eval().set_feats_bf16(True)
+    with torch.no_grad():
+        got = cat.sweep(t(feats, dev), t(g0[None], dev), None).cpu().numpy()
+    assert relmax(got, orc.sweep_concat(orc.bf16_round(feats), g0[None])) <= TOL
+    assert relmax(got, orc.sweep_concat(feats, g0[None])) <= BF16_TOL
+
+
 def test_candidate_sharded_sweep_two_gpus(dev):
     """NCCL all-gather variant and the fused peer-store variant on 2 GPUs of one box (skipped on a 1-GPU box)."""
     import json
