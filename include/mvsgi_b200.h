@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MVSGI_ABI_VERSION 6
+#define MVSGI_ABI_VERSION 7
 #define MVSGI_MAX_CAMS 4
 #define MVSGI_MAX_CANDS 64
 #define MVSGI_MAX_PEERS 7 /* extra destinations of a candidate-sharded sweep (8 GPUs of one box) */
@@ -265,6 +265,35 @@ typedef struct MvsgiSoftArgminBwdArgs {
   int64_t grad_costs_stride[4];   /* B, D, H, W */
 } MvsgiSoftArgminBwdArgs;
 int mvsgi_softargmin_backward_f32(const MvsgiSoftArgminBwdArgs* args, void* cuda_stream);
+
+/* ---- fisheye -> surrogate-ERP image resampling (the step before the feature extractor) -------------------------- */
+/* Replaces CameraModelRotation (dsta_mvs/image_sampler/camera_model_sampler.py:12-120) as
+ * InferencePytorch.preprocess_imgs drives it (api/inference_pytorch.py:61-74): every pixel of the target
+ * (Equirectangular surrogate) image is a ray, rotated into the raw camera by R_raw_fisheye, projected with the raw
+ * camera model and bilinearly sampled (F.grid_sample, zeros padding, align_corners=False); pixels whose ray the raw
+ * camera cannot see get invalid_value.  The geometry is evaluated in-kernel from `rig`:
+ *   cv_width/cv_height/cv_lon0/cv_lon_span_pixel/cv_lat0/cv_lat_range = the TARGET Equirectangular model,
+ *   num_cams = 1, cams[0] = the RAW camera model with rot = R_raw_fisheye (row-major) and trans = 0,
+ *   num_cands = 1, dist[0] = 1.
+ * All `batch` images share that geometry (same camera model and orientation, e.g. consecutive frames). */
+#define MVSGI_RESAMPLE_IMG_U8 1u /* img holds uint8 pixels; each tap is scaled to [0,1] on load exactly as the CUDA
+                                  * `t_imgs.float() / 255.0` of preprocess_imgs (api/inference_pytorch.py:56-57)
+                                  * does it: v * float32(1/255) */
+typedef struct MvsgiResampleArgs {
+  uint32_t struct_size;
+  uint32_t flags;          /* 0 or MVSGI_RESAMPLE_IMG_U8 */
+  int32_t batch, channels;
+  int32_t in_h, in_w;      /* raw image size; must equal rig->cams[0].height/width */
+  const void* img;         /* float32 (or uint8) element (n, c, y, x) at the given ELEMENT strides: an NCHW tensor, or the
+                            * permuted view of the HWC camera buffers (api/inference_pytorch.py:55) without a copy */
+  int64_t img_stride[4];   /* N, C, H, W */
+  const MvsgiRig* rig;     /* HOST pointer */
+  float invalid_value;     /* default_invalid_value of the reference sampler (0) */
+  int32_t reserved;
+  float* out;              /* [batch, channels, cv_height, cv_width] contiguous */
+  uint8_t* valid_out;      /* optional [cv_height, cv_width]: 1 where the raw camera sees the ray */
+} MvsgiResampleArgs;
+int mvsgi_resample_f32(const MvsgiResampleArgs* args, void* cuda_stream);
 
 /* ---- peer-mapped volumes for the candidate-sharded sweep ------------------- */
 /* One process per GPU.  Each rank allocates its copy of the volume with mvsgi_p2p_alloc (cudaMalloc on the current

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_CAMS = 4
 MAX_CANDS = 64
 MAX_PEERS = 7
@@ -24,6 +24,7 @@ FLAG_FEATS_BF16 = 1
 FLAG_STAGE_ONLY = 2
 FLAG_SWEEP_ONLY = 4
 FLAG_VOL_CHANNELS_LAST = 8
+RESAMPLE_IMG_U8 = 1
 
 LIB_NAME = "libmvsgi_b200.so"
 _PKG_DIR = Path(__file__).resolve().parent
@@ -105,6 +106,24 @@ class MvsgiProjectArgs(C.Structure):
     ]
 
 
+class MvsgiResampleArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("batch", C.c_int32),
+        ("channels", C.c_int32),
+        ("in_h", C.c_int32),
+        ("in_w", C.c_int32),
+        ("img", C.c_void_p),
+        ("img_stride", C.c_int64 * 4),
+        ("rig", C.POINTER(MvsgiRig)),
+        ("invalid_value", C.c_float),
+        ("reserved", C.c_int32),
+        ("out", C.c_void_p),
+        ("valid_out", C.c_void_p),
+    ]
+
+
 class MvsgiSoftArgminArgs(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32),
@@ -157,6 +176,7 @@ EXPORTS = {
     "mvsgi_sweep_f32": (C.c_int, [C.POINTER(MvsgiSweepArgs), C.c_void_p]),
     "mvsgi_sweep_launch_count": (C.c_int, [C.POINTER(MvsgiSweepArgs)]),
     "mvsgi_project_only_f32": (C.c_int, [C.POINTER(MvsgiProjectArgs), C.c_void_p]),
+    "mvsgi_resample_f32": (C.c_int, [C.POINTER(MvsgiResampleArgs), C.c_void_p]),
     "mvsgi_mask_pitch_words": (C.c_int32, [C.c_int32]),
     "mvsgi_pack_masks": (
         C.c_int,

@@ -10,6 +10,7 @@
 #include "sweep.cuh"
 #include "sweep_walk.cuh"
 #include "backward.cuh"
+#include "resample.cuh"
 
 namespace {
 
@@ -486,6 +487,48 @@ int mvsgi_project_only_f32(const MvsgiProjectArgs* a, void* stream) {
     return MVSGI_E_SHAPE;
   const int n = r.cv_width * r.cv_height;
   mvsgi::project_only_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r, a->grids, a->grid_masks);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int mvsgi_resample_f32(const MvsgiResampleArgs* a, void* stream) {
+  if (a == nullptr || a->rig == nullptr || a->img == nullptr || a->out == nullptr) return MVSGI_E_NULL;
+  if (a->struct_size != sizeof(MvsgiResampleArgs)) return MVSGI_E_VERSION;
+  if (a->flags & ~MVSGI_RESAMPLE_IMG_U8) return MVSGI_E_UNSUPPORTED;
+  const MvsgiRig& r = *a->rig;
+  if (r.num_cams != 1 || r.num_cands != 1 || r.dist[0] != 1.0f) return MVSGI_E_SHAPE;
+  if (r.cams[0].model < 0 || r.cams[0].model > MVSGI_CAM_LINEAR_SPHERE) return MVSGI_E_UNSUPPORTED;
+  if (a->batch < 1 || a->channels < 1 || a->in_h < 1 || a->in_w < 1 || r.cv_width < 1 || r.cv_height < 1)
+    return MVSGI_E_SHAPE;
+  if (a->in_h != r.cams[0].height || a->in_w != r.cams[0].width) return MVSGI_E_SHAPE;  // check_input_shape :92-96
+  if ((int64_t)r.cv_width * r.cv_height >= (1ll << 31)) return MVSGI_E_SHAPE;
+  mvsgi::ResampleKP kp;
+  kp.N = a->batch; kp.C = a->channels; kp.H = a->in_h; kp.W = a->in_w; kp.Ht = r.cv_height; kp.Wt = r.cv_width;
+  kp.img = a->img;
+  kp.sN = a->img_stride[0]; kp.sC = a->img_stride[1]; kp.sH = a->img_stride[2]; kp.sW = a->img_stride[3];
+  kp.invalid = a->invalid_value;
+  kp.out = a->out;
+  kp.validOut = a->valid_out;
+  // the geometry is evaluated once per thread and reused for its images: split the batch over blockIdx.y only as far as
+  // needed to fill the GPU
+  const int blocks = ((kp.Wt + 31) / 32) * ((kp.Ht + mvsgi::kResampleThreads / 32 - 1) / (mvsgi::kResampleThreads / 32));
+  int gy = 1;
+  while (blocks * gy < device_sms() * 16 && gy * 2 <= a->batch && gy < 64) gy *= 2;
+  const int gy_env = env_int("MVSGI_RESAMPLE_GY", 0);
+  if (gy_env > 0) gy = gy_env < a->batch ? gy_env : a->batch;
+  dim3 grid(blocks, gy);
+  const bool u8 = (a->flags & MVSGI_RESAMPLE_IMG_U8) != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->channels % 3 == 0) {
+    if (u8) mvsgi::resample_kernel<3, uint8_t><<<grid, mvsgi::kResampleThreads, 0, st>>>(kp, r);
+    else mvsgi::resample_kernel<3, float><<<grid, mvsgi::kResampleThreads, 0, st>>>(kp, r);
+  } else if (a->channels % 4 == 0) {
+    if (u8) mvsgi::resample_kernel<4, uint8_t><<<grid, mvsgi::kResampleThreads, 0, st>>>(kp, r);
+    else mvsgi::resample_kernel<4, float><<<grid, mvsgi::kResampleThreads, 0, st>>>(kp, r);
+  } else {
+    if (u8) mvsgi::resample_kernel<1, uint8_t><<<grid, mvsgi::kResampleThreads, 0, st>>>(kp, r);
+    else mvsgi::resample_kernel<1, float><<<grid, mvsgi::kResampleThreads, 0, st>>>(kp, r);
+  }
   g_launches++;
   return (int)cudaGetLastError();
 }

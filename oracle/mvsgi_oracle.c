@@ -523,6 +523,60 @@ void orc_make_grids_f64(const MvsgiRig* rig, double* grids, uint8_t* grid_masks)
         }
 }
 
+/* ------------------------------------------------------------------------- */
+/* Fisheye -> surrogate-ERP resampling.
+ * CameraModelRotation  dsta_mvs/image_sampler/camera_model_sampler.py:55-75 (grid), :98-120 (__call__):
+ *   rays of the target pixels (Equirectangular.pixel_2_ray at pixel centres, planar_as_base.py:200-201),
+ *   x_raw = R_raw_fisheye @ x (planar_as_base.py:206-209), raw.point_3d_2_pixel(normalized=True),
+ *   invalid -> grid = -1 and the output pixel = invalid value (:67-71, :117),
+ *   F.grid_sample(bilinear, zeros, align_corners=False) (:110-114).
+ * rig: cv_* = target model, cams[0] = raw model with rot = R_raw_fisheye, trans = 0, dist[0] = 1.
+ * img [N,C,H,W] contiguous -> out [N,C,Ht,Wt], valid [Ht,Wt].
+ * grid_in/valid_in (optional, [Ht,Wt,2] / [Ht,Wt]): sample with this grid instead of evaluating the geometry here —
+ * how the tests hand the oracle the CUDA kernel's own grid (SURVEY.md section 8c criterion 3b). */
+void orc_resample(const MvsgiRig* rig, const float* img, int N, int C, int H, int W, float invalid, float* out,
+                  uint8_t* valid_out, const float* grid_in, const uint8_t* valid_in) {
+  const int Ht = rig->cv_height, Wt = rig->cv_width;
+  const MvsgiCamera* c = &rig->cams[0];
+#pragma omp parallel for schedule(static)
+  for (int h = 0; h < Ht; ++h)
+    for (int w = 0; w < Wt; ++w) {
+      float ray[3], gx, gy;
+      int valid;
+      orc_cv_ray(rig, h, w, ray);
+      float x = (c->rot[0] * ray[0] + c->rot[1] * ray[1]) + c->rot[2] * ray[2];
+      float y = (c->rot[3] * ray[0] + c->rot[4] * ray[1]) + c->rot[5] * ray[2];
+      float z = (c->rot[6] * ray[0] + c->rot[7] * ray[1]) + c->rot[8] * ray[2];
+      orc_project(c, x, y, z, &gx, &gy, &valid);
+      if (grid_in) {
+        gx = grid_in[((int64_t)h * Wt + w) * 2];
+        gy = grid_in[((int64_t)h * Wt + w) * 2 + 1];
+        valid = valid_in[(int64_t)h * Wt + w] != 0;
+      }
+      if (valid_out) valid_out[(int64_t)h * Wt + w] = (uint8_t)valid;
+      /* grid_sample: unnormalise (align_corners=False), 4 taps, out-of-bounds taps contribute 0 */
+      float fx = ((gx + 1.0f) * (float)W - 1.0f) * 0.5f, fy = ((gy + 1.0f) * (float)H - 1.0f) * 0.5f;
+      float x0f = floorf(fx), y0f = floorf(fy);
+      float wnw = (x0f + 1.0f - fx) * (y0f + 1.0f - fy), wne = (fx - x0f) * (y0f + 1.0f - fy);
+      float wsw = (x0f + 1.0f - fx) * (fy - y0f), wse = (fx - x0f) * (fy - y0f);
+      int inr = valid && fx > -1.0f && fx < (float)W && fy > -1.0f && fy < (float)H;
+      long x0 = inr ? (long)x0f : 0, y0 = inr ? (long)y0f : 0;
+      for (int n = 0; n < N; ++n)
+        for (int ch = 0; ch < C; ++ch) {
+          const float* im = img + ((int64_t)n * C + ch) * H * W;
+          float v = invalid;
+          if (valid) {
+            float nw = (inr && x0 >= 0 && y0 >= 0) ? im[y0 * W + x0] : 0.0f;
+            float ne = (inr && x0 + 1 < W && y0 >= 0) ? im[y0 * W + x0 + 1] : 0.0f;
+            float sw = (inr && x0 >= 0 && y0 + 1 < H) ? im[(y0 + 1) * W + x0] : 0.0f;
+            float se = (inr && x0 + 1 < W && y0 + 1 < H) ? im[(y0 + 1) * W + x0 + 1] : 0.0f;
+            v = ((nw * wnw + ne * wne) + sw * wsw) + se * wse;
+          }
+          out[(((int64_t)n * C + ch) * Ht + h) * Wt + w] = v;
+        }
+    }
+}
+
 int orc_num_threads(void) {
 #if defined(_OPENMP)
   return omp_get_max_threads();

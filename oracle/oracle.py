@@ -184,3 +184,20 @@ def bf16_round(a: np.ndarray) -> np.ndarray:
     u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
     r = ((u >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
     return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
+
+
+def resample(rig_struct: abi.MvsgiRig, img, invalid_value: float = 0.0, grid=None, grid_valid=None):
+    """CameraModelRotation (camera_model_sampler.py:55-120): img [N,C,H,W] -> (out [N,C,Ht,Wt], valid [Ht,Wt] bool).
+    rig_struct as built by mvs_gi_b200.resample.resample_rig.  `grid` [Ht,Wt,2] + `grid_valid` [Ht,Wt]: sample with
+    this grid (the CUDA kernel's own, from mvsgi_project_only) instead of the one evaluated here."""
+    img = _f32(img)
+    N, Cc, H, W = img.shape
+    Ht, Wt = rig_struct.cv_height, rig_struct.cv_width
+    out = np.empty((N, Cc, Ht, Wt), np.float32)
+    valid = np.empty((Ht, Wt), np.uint8)
+    if grid is not None:
+        grid = _f32(grid).reshape(Ht, Wt, 2)
+        grid_valid = np.ascontiguousarray(np.asarray(grid_valid).reshape(Ht, Wt), dtype=np.uint8)
+    lib().orc_resample(C.byref(rig_struct), _p(img), N, Cc, H, W, C.c_float(invalid_value), _p(out), _p(valid),
+                       _p(grid), _p(grid_valid))
+    return out, valid.astype(bool)

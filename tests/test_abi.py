@@ -33,10 +33,12 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_ctypes_structs_match_the_c_layout(tmp_path):
-    structs = ["MvsgiCamera", "MvsgiRig", "MvsgiSweepArgs", "MvsgiProjectArgs", "MvsgiSoftArgminArgs"]
+    structs = ["MvsgiCamera", "MvsgiRig", "MvsgiSweepArgs", "MvsgiProjectArgs", "MvsgiSoftArgminArgs",
+               "MvsgiResampleArgs"]
     probes = {"MvsgiSweepArgs": ["feats", "masks", "grids", "rig", "vol", "workspace", "cand_offset", "peer_vols"],
               "MvsgiSoftArgminArgs": ["costs", "inv_dist_idx", "argmax"], "MvsgiRig": ["cams", "dist"],
-              "MvsgiCamera": ["rot", "p"], "MvsgiProjectArgs": ["rig", "grid_masks"]}
+              "MvsgiCamera": ["rot", "p"], "MvsgiProjectArgs": ["rig", "grid_masks"],
+              "MvsgiResampleArgs": ["img", "img_stride", "rig", "invalid_value", "out", "valid_out"]}
     src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
     for s in structs:
         src.append(f'printf("{s} %zu\\n", sizeof({s}));')
