@@ -645,3 +645,19 @@ def test_softargmin_backward_vs_oracle_and_torch(dev):
     inv_t = torch.sum(p * reg.inv_dist_idx.expand_as(p), 1, keepdim=True)
     (gt,) = torch.autograd.grad([inv_t, p], c2, [g_inv, g_nc])
     assert relmax(g.cpu().numpy(), gt.cpu().numpy()) <= TOL
+    # more candidates than one shared-memory chunk (40 > 16), x3 upsample, sizes that divide no tile, batch 3,
+    # and only one of the two upstream gradients present
+    from mvs_gi_b200 import calibration as cal
+    for D, scale, hw in [(40, 3, (7, 71)), (64, 2, (5, 33)), (3, 2, (1, 1))]:
+        reg2 = modules.DistanceRegressorWithFixedCandidates(96, cal.dist_inverse_spaced(D), scale, True).to(dev)
+        cn = (np.random.default_rng(D).standard_normal((3, 1, D, *hw)) * 3).astype(np.float32)
+        c3 = t(cn, dev).requires_grad_(True)
+        inv3, nc3 = reg2(c3)
+        gi3, gn3 = torch.randn_like(inv3), torch.randn_like(nc3)
+        (g3,) = torch.autograd.grad([inv3, nc3], c3, [gi3, gn3], retain_graph=True)
+        ref3 = orc.softargmin_backward(cn, reg2.inv_dist_idx.cpu().numpy(), scale, True, gi3.cpu().numpy(),
+                                       gn3.cpu().numpy())
+        assert relmax(g3.cpu().numpy(), ref3) <= TOL, (D, scale)
+        (g4,) = torch.autograd.grad([inv3], c3, [gi3])
+        ref4 = orc.softargmin_backward(cn, reg2.inv_dist_idx.cpu().numpy(), scale, True, gi3.cpu().numpy(), None)
+        assert relmax(g4.cpu().numpy(), ref4) <= TOL, (D, scale, "inv only")
