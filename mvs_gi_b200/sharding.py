@@ -245,17 +245,22 @@ class CandidateShardedSweep(torch.nn.Module):
             Ho, Wo = self.full_rig.cv_camera.H, self.full_rig.cv_camera.W
         else:
             Ho, Wo = g.shape[3:5]
-        shape = (B, cout, D, Ho, Wo)
+        # channels-last volume (builder.set_vol_channels_last): the peer buffers hold [B, D, Ho, Wo, C] and the module
+        # sees the permuted [B, C, D, Ho, Wo] view; a warp's peer store is then 512 contiguous bytes over NVLink
+        cl = bool(getattr(b, "vol_channels_last", False))
+        shape = (B, D, Ho, Wo, cout) if cl else (B, cout, D, Ho, Wo)
         if self._peer_volume is None or self._peer_volume.shape != shape:
             if self._peer_volume is not None:
                 self._peer_volume.close()
             self._peer_volume = PeerVolume(shape, feats.device, self.group)
             self._flag = torch.zeros(1, device=feats.device)
         vol, peers = self._peer_volume.next()
+        if cl:
+            vol = vol.permute(0, 4, 1, 2, 3)
         if std and b._static_masks is not None:
             masks = b._static_masks
         call = ops.SweepCall(feats, g, gm, masks if std else None, b._rig_blob, b._aggregate, Ho, Wo, d1 - d0,
-                             out=vol, cand_offset=d0, peer_ptrs=peers)
+                             out=vol, cand_offset=d0, peer_ptrs=peers, channels_last=cl)
         call.run()
         if world > 1:
             # stream-ordered rendezvous: it starts after this rank's sweep kernel and ends when every rank has joined,

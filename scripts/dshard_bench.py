@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--small", action="store_true", help="shrunken shapes (tests)")
+    ap.add_argument("--channels-last", action="store_true", help="channels_last_3d volume (512-byte peer stores)")
     args = ap.parse_args()
     from mvs_gi_b200 import modules, sharding, synthetic
 
@@ -48,6 +49,9 @@ def main():
         modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval(), rig)
     fused = sharding.CandidateShardedSweep(
         modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval(), rig, fused=True)
+    if args.channels_last:
+        for m in (full, shard.builder, fused.builder):
+            m.set_vol_channels_last(True)
     d0, d1 = sharding.candidate_shard(w.num_cands)
 
     def timed(fn, n):
@@ -81,7 +85,7 @@ def main():
         vol_bytes = vol_full.numel() * 4
         recv = vol_bytes * (world - 1) / world
         print(json.dumps({
-            "what": "candidate-sharded sweep", "workload": w.name, "n_gpus": world, "batch": B,
+            "what": "candidate-sharded sweep", "workload": w.name, "channels_last": bool(args.channels_last), "n_gpus": world, "batch": B,
             "bit_identical_to_unsharded_on_all_ranks": bool(ok.item()),
             "ms_unsharded_one_gpu": ms_full, "ms_sharded_total": ms_sharded, "ms_local_slice_sweep": ms_local,
             "ms_allgather_and_reassemble": ms_gather, "ms_fused_p2p_total": ms_fused, "ms_rendezvous_allreduce": ms_rdv,
