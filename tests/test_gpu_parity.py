@@ -402,6 +402,48 @@ def test_bf16_staged_features_stated_tolerance(dev):
     assert relmax(got, orc.sweep_concat(feats, g0[None])) <= BF16_TOL
 
 
+def test_cuda_graph_capture_and_replay(dev):
+    """The C ABI neither allocates nor synchronises, so a whole step (staging, mask packing, sweep, soft-argmin) and a
+    backward call capture into a CUDA graph; replays on new input values reproduce the eager results bit for bit."""
+    from mvs_gi_b200 import abi, modules, ops
+
+    w, feats, _, masks = _case("G16V", 2, 91, feat_hw=(24, 96), mask_hw=(96, 384), cv_hw=(12, 72), n_cands=7)
+    rig = w.rig()
+    blob = ops.rig_to_blob(rig.to_struct())
+    f, mk = t(feats, dev), t(masks, dev)
+    reg = modules.DistanceRegressorWithFixedCandidates(w.bf, w.dist_list, 2, True).to(dev)
+    costs = torch.randn((2, 1, w.num_cands, *w.cv_hw), device=dev)
+    call = ops.SweepCall(f, None, None, mk, blob, abi.AGG_STD, *w.cv_hw, w.num_cands, channels_last=True)
+    gvol = torch.randn_like(call.vol)
+
+    def step():
+        call.run()
+        inv, _, _ = ops.softargmin_op(costs, reg.inv_dist_idx, 24, 144, 0.5, False, False)
+        gf = ops.sweep_backward_op(gvol, f, None, None, mk, blob, abi.AGG_CONCAT if False else abi.AGG_STD, *w.cv_hw,
+                                   w.num_cands)
+        return inv, gf
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_inv, g_gf = step()
+    for seed in (1, 2):
+        torch.manual_seed(seed)
+        f.copy_(torch.randn_like(f))
+        costs.copy_(torch.randn_like(costs))
+        graph.replay()
+        torch.cuda.synchronize()
+        got_vol, got_inv, got_gf = call.vol.clone(), g_inv.clone(), g_gf.clone()
+        inv, gf = step()
+        assert torch.equal(call.vol, got_vol) and torch.equal(inv, got_inv)
+        # fp32 atomics: the gradient is order-dependent in the last bits
+        assert float((gf - got_gf).abs().max()) <= 1e-5 * float(gf.abs().max())
+
+
 def test_candidate_sharded_sweep_two_gpus(dev):
     """NCCL all-gather variant and the fused peer-store variant on 2 GPUs of one box (skipped on a 1-GPU box)."""
     import json
