@@ -313,7 +313,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         const uint32_t* rec = tab + (size_t)min(jw + q8, npairs - 1) * ES;
         const int po = (int)rec[0];
         const bool act = jw + q8 < npairs && po >= 0;
-        const uint32_t v = (rec[1] >> vsh) & 0xFFu;
+        const uint32_t v = reinterpret_cast<const unsigned char*>(rec + 1)[vsh >> 3];  // this frame's byte only: the other byte is being rewritten for the next frame
         const int n = __popc(v);
         const bool need = act && (AGG == MVSGI_AGG_CONCAT || n > 1);  // spherical_sweep_avg.py:106-111
         const FT* fcg = fbq;

@@ -170,7 +170,7 @@ sweep_walk_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
             const uint32_t* rec = rec0 + i * ES;
             const int po = (int)rec[0];
             const bool act = po >= 0;
-            const uint32_t v = (rec[1] >> vsh) & 0xFFu;
+            const uint32_t v = reinterpret_cast<const unsigned char*>(rec + 1)[vsh >> 3];  // this frame's byte only: the other byte is being rewritten for the next frame
             const int n = __popc(v);
             const bool need = act && (AGG == MVSGI_AGG_CONCAT || n > 1);  // spherical_sweep_avg.py:106-111
             float wEt[CAM], wEb[CAM], wOt[CAM], wOb[CAM];
