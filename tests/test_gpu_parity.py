@@ -488,6 +488,75 @@ def test_errors_are_loud(dev):
                               torch.ones(1, 3, 1, 8, 8, device=dev), None, abi.AGG_STD, 4, 4, 2)
 
 
+def test_camera_counts_candidate_limits_and_tiny_shapes(dev):
+    """Edges of the supported range against the oracle: 1 and 2 cameras (std with one camera is all zero: n > 1 never
+    holds, spherical_sweep_avg.py:106-111), the maximum of 64 in-kernel candidates, a single frame, a 1 x 1 cost
+    volume, features of one pixel, and more candidates than MVSGI_MAX_CANDS (must be refused in fused mode)."""
+    import copy
+
+    from mvs_gi_b200 import calibration as cal
+    from mvs_gi_b200 import modules, ops, synthetic
+    from oracle import oracle as orc
+
+    base = synthetic.small(synthetic.WORKLOADS["4CAM"], feat_hw=(12, 40), mask_hw=(24, 80), cv_hw=(6, 21), n_cands=5)
+    for ncam in (1, 2):
+        w = copy.copy(base)
+        w.num_cams = ncam
+        rig = w.rig()
+        feats = synthetic.make_feats(w, 2, 100 + ncam)
+        masks = synthetic.erase_rectangles(synthetic.fisheye_footprint_masks(w), 2, 7)
+        g, gm = orc.make_grids(rig.to_struct())
+        for cl in (False, True):
+            m = modules.SphericalSweepStdMasked(ncam, w.feat_chs, 3).to(dev).eval().attach_rig(rig)
+            m.set_vol_channels_last(cl)
+            with torch.no_grad():
+                vol, valid = m.sweep_with_valid(t(feats, dev), None, None, t(masks, dev))
+                kg, kgm = ops.project_only(rig.to_struct(), dev)
+            ref, ref_valid = orc.sweep_std(feats, kg.cpu().numpy()[None], kgm.cpu().numpy()[None], masks,
+                                           return_valid=True)
+            assert np.array_equal(valid.cpu().numpy(), ref_valid)
+            assert np.array_equal(vol.cpu().numpy() == 0, ref == 0)
+            if ncam == 1:
+                assert not ref_valid.any() and float(vol.abs().max()) == 0.0
+            else:
+                assert ref_valid.any() and relmax(vol.cpu().numpy(), ref) <= TOL
+            cat = modules.SphericalSweep(ncam, ncam * w.feat_chs, 3).to(dev).eval().set_vol_channels_last(cl)
+            with torch.no_grad():
+                cv = cat.sweep(t(feats, dev), t(g[None], dev), None)
+            assert relmax(cv.cpu().numpy(), orc.sweep_concat(feats, g[None])) <= TOL
+    # 64 candidates evaluated in-kernel, one frame; then 65: refused
+    w = copy.copy(base)
+    w.num_cams = 3
+    w.dist_list = cal.dist_inverse_spaced(64)
+    rig = w.rig()
+    feats = synthetic.make_feats(w, 1, 5)
+    masks = synthetic.fisheye_footprint_masks(w)[None]
+    m = modules.SphericalSweepStdMasked(3, w.feat_chs, 3).to(dev).eval().attach_rig(rig)
+    with torch.no_grad():
+        vol = m.sweep(t(feats, dev), None, None, t(masks, dev))
+        kg, kgm = ops.project_only(rig.to_struct(), dev)
+    ref = orc.sweep_std(feats, kg.cpu().numpy()[None], kgm.cpu().numpy()[None], masks)
+    assert vol.shape[2] == 64 and np.array_equal(vol.cpu().numpy() == 0, ref == 0)
+    assert relmax(vol.cpu().numpy(), ref) <= TOL
+    with pytest.raises(ValueError, match="candidates"):
+        cal.Rig(rig.cv_camera, rig.cameras, rig.poses_cv_cam, cal.dist_inverse_spaced(65))
+    # supplied grids have no candidate limit: 70 candidates, 1 x 1 cost volume, 1 x 1 features
+    gen = np.random.default_rng(9)
+    feats1 = gen.standard_normal((2, 3, 16, 1, 1)).astype(np.float32)
+    grids1 = gen.uniform(-1.2, 1.2, (2, 3, 70, 1, 1, 2)).astype(np.float32)
+    cat = modules.SphericalSweep(3, 48, 3).to(dev).eval()
+    with torch.no_grad():
+        cv = cat.sweep(t(feats1, dev), t(grids1, dev), None)
+    assert cv.shape == (2, 48, 70, 1, 1) and relmax(cv.cpu().numpy(), orc.sweep_concat(feats1, grids1)) <= TOL
+    gm1 = gen.uniform(0, 1, (2, 3, 70, 1, 1)) > 0.3
+    masks1 = np.ones((2, 3, 1, 2, 3), np.float32)
+    std = modules.SphericalSweepStdMasked(3, 16, 3).to(dev).eval()
+    with torch.no_grad():
+        sv = std.sweep(t(feats1, dev), t(grids1, dev), t(gm1[..., None], dev), t(masks1, dev))
+    ref = orc.sweep_std(feats1, grids1, gm1, masks1)
+    assert np.array_equal(sv.cpu().numpy() == 0, ref == 0) and relmax(sv.cpu().numpy(), ref) <= TOL
+
+
 # ------------------------------------------------------------------ 3. full-size properties (BASELINE.json shapes)
 @pytest.mark.parametrize("name,B", [("G16V", 4), ("4CAM", 2), ("HIGHD", 1)])
 def test_full_size_std_properties(dev, name, B):
