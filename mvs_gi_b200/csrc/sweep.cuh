@@ -100,9 +100,12 @@ MVSGI_DEV MaskWords mask_fetch(const uint32_t* __restrict__ img, uint32_t info, 
   const uint32_t word = (info & 0x0FFFFFFFu) >> 5;
   MaskWords m;
   m.a = __ldg(img + word);
-  m.b = __ldg(img + word + 1);
   m.c = __ldg(img + word + mPitch);
-  m.d = __ldg(img + word + mPitch + 1);
+  m.b = m.d = 0u;
+  if ((info & 31u) == 31u) {  // only then does tap x0 + 1 live in the next word (1 lookup in 32)
+    m.b = __ldg(img + word + 1);
+    m.d = __ldg(img + word + mPitch + 1);
+  }
   return m;
 }
 MVSGI_DEV uint32_t mask_eval(const MaskWords& m, uint32_t info) {
