@@ -191,9 +191,11 @@ typedef struct MvsgiProjectArgs {
 int mvsgi_project_only_f32(const MvsgiProjectArgs* args, void* cuda_stream);
 
 /* ---- mask packing -------------------------------------------------------- */
-/* Packs masks (>0 -> 1) into the padded bit layout the sweep samples:
- * per (n) image: (Hm+2) rows x pitch_words uint32; pixel (y, x) is bit (x & 31) of word 1 + (x >> 5) of row y + 1
- * (row 0, row Hm+1, word 0 and the words after the data are zero guards).
+/* Packs masks (>0 -> 1) into the padded bit layout the sweep samples.  Per image: (Hm+2) row PAIRS x pitch_words x 2
+ * uint32; pair Y holds padded rows Y (even word of each couple) and Y+1 (odd word), so the two mask rows of a bilinear
+ * sample are one 8-byte load; pixel (y, x) is bit (x & 31) of word 1 + (x >> 5) of padded row y + 1 (row 0, row Hm+1,
+ * word 0 and the words after the data are zero guards).  bits_out holds n_images * (Hm+2) * pitch_words * 2 words and
+ * must be 8-byte aligned.
  * flags_out[0] gets bit0 set if any mask value is negative or NaN (then the
  * "bilinear(mask) > 0" test of spherical_sweep_avg.py:92-96 is not equivalent
  * to the packed test and the caller should reject the input). */

@@ -115,7 +115,7 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
                        (a->grids_stride[0] != 0 || (std_agg && a->grid_masks_stride[0] != 0));
   p->n_mask_images = std_agg ? (p->per_frame_masks ? a->batch : 1) * a->num_cams : 0;
   p->mask_pitch = std_agg ? mask_pitch_words(a->mask_w) : 0;
-  p->mask_words = std_agg ? (a->mask_h + 2) * p->mask_pitch : 0;
+  p->mask_words = std_agg ? (a->mask_h + 2) * p->mask_pitch * 2 : 0;  // row pairs, each row stored twice (stage.cuh)
   p->feats_bytes = align_up((int64_t)a->batch * a->num_cams * p->cg * (a->feat_h + 3) * (a->feat_w + 2) * mvsgi::kCG *
                                 ((a->flags & MVSGI_FLAG_FEATS_BF16) ? 2 : 4), 256);
   p->mask_bytes = align_up((int64_t)p->n_mask_images * p->mask_words * 4 + 16, 256);  // +16: funnel-shift over-read

@@ -91,7 +91,8 @@ stage_feats_kernel(const float* __restrict__ src, long long sN0, int n1, long lo
 
 // One block packs one padded row of one mask image: every lane reads 4 consecutive mask pixels (one 16-byte load when
 // VEC), turns them into a nibble, and 8 lanes OR their nibbles into a word with three shuffles.
-// Bit layout: padded row Y = y + 1 (rows 0 and Hm + 1 are zero); word 0 of a row is a zero guard, pixel x is bit
+// Bit layout: padded row Y = y + 1 (rows 0 and Hm + 1 are zero), rows stored as interleaved pairs (below); word 0 of
+// a row is a zero guard, pixel x is bit
 // (x & 31) of word 1 + (x >> 5), and at least one zero guard word follows, so taps x0 = -1 and x0 + 1 = Wm read zeros.
 // flags[0] bit0 is set when any mask value is negative or NaN (then the packed test is not equivalent to the
 // reference's float test and the caller must reject the input).
@@ -117,14 +118,23 @@ __global__ void __launch_bounds__(kPackThreads)
 pack_masks_kernel(const T* __restrict__ src, int n1, long long sN0, long long sN1, long long sH, long long sW, int Hm,
                   int Wm, int pitch, uint32_t* __restrict__ bits, int* __restrict__ flags) {
   const int n = blockIdx.y, Y = blockIdx.x, t = threadIdx.x, lane = t & 31;
-  uint32_t* row = bits + ((long long)n * (Hm + 2) + Y) * pitch;
+  // row-pair interleaved: word j of padded row Y is stored as the TOP of pair Y and as the BOTTOM of pair Y - 1, so
+  // the two rows a bilinear mask sample needs are one aligned 8-byte load (sweep.cuh, mask_fetch)
+  uint32_t* img = bits + (long long)n * (Hm + 2) * pitch * 2;
+  auto put = [&](int j, uint32_t w) {
+    img[((long long)Y * pitch + j) * 2] = w;
+    if (Y > 0) img[((long long)(Y - 1) * pitch + j) * 2 + 1] = w;
+  };
   const int dataWords = (Wm + 31) >> 5;
   if (Y == 0 || Y == Hm + 1) {
-    for (int j = t; j < pitch; j += kPackThreads) row[j] = 0u;
+    for (int j = t; j < pitch; j += kPackThreads) {
+      put(j, 0u);
+      if (Y == Hm + 1) img[((long long)Y * pitch + j) * 2 + 1] = 0u;  // bottom of the last pair: never a real row
+    }
     return;
   }
-  if (t == 0) row[0] = 0u;
-  for (int j = 1 + dataWords + t; j < pitch; j += kPackThreads) row[j] = 0u;
+  if (t == 0) put(0, 0u);
+  for (int j = 1 + dataWords + t; j < pitch; j += kPackThreads) put(j, 0u);
   const T* s = src + (long long)(n / n1) * sN0 + (long long)(n % n1) * sN1 + (long long)(Y - 1) * sH;
   bool bad = false;
   constexpr int U = 4;  // row segments per thread with all loads issued before the first use (kPackThreads * 16 pixels per pass)
@@ -158,7 +168,7 @@ pack_masks_kernel(const T* __restrict__ src, int n1, long long sN0, long long sN
       w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
       w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
       w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
-      if ((lane & 7) == 0 && (x0 >> 5) < dataWords) row[1 + (x0 >> 5)] = w;
+      if ((lane & 7) == 0 && (x0 >> 5) < dataWords) put(1 + (x0 >> 5), w);
     }
   }
   if (__any_sync(0xFFFFFFFFu, bad) && lane == 0 && flags != nullptr) atomicOr(flags, 1);

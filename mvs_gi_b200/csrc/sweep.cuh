@@ -98,13 +98,17 @@ struct MaskWords {
 };
 MVSGI_DEV MaskWords mask_fetch(const uint32_t* __restrict__ img, uint32_t info, int mPitch) {
   const uint32_t word = (info & 0x0FFFFFFFu) >> 5;
+  // packed rows are stored as interleaved pairs (stage.cuh): one 8-byte load = word `word` of rows Y0 and Y0 + 1
+  const uint2* pairs = reinterpret_cast<const uint2*>(img);
   MaskWords m;
-  m.a = __ldg(img + word);
-  m.c = __ldg(img + word + mPitch);
+  const uint2 ac = __ldg(pairs + word);
+  m.a = ac.x;
+  m.c = ac.y;
   m.b = m.d = 0u;
   if ((info & 31u) == 31u) {  // only then does tap x0 + 1 live in the next word (1 lookup in 32)
-    m.b = __ldg(img + word + 1);
-    m.d = __ldg(img + word + mPitch + 1);
+    const uint2 bd = __ldg(pairs + word + 1);
+    m.b = bd.x;
+    m.d = bd.y;
   }
   return m;
 }
