@@ -147,7 +147,10 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   p->max_pairs = p->run_len * dch;
   p->grid = p->num_items < grid_target ? p->num_items : grid_target;
   p->interleave = env_int("MVSGI_INTERLEAVE", 1) ? 1 : 0;
-  p->group_px = env_int("MVSGI_GROUP_PX", p->interleave ? 8 : 32);
+  // order of the (candidate, pixel) records inside a run: with interleaved runs one group = the whole run, i.e.
+  // candidate-major over all of the run's octets (measured against groups of 8 px: G16V -3.5 %, 4 cameras -19 %,
+  // C=48 -11 %, DoubleSphere -16 %, high-D +1 %)
+  p->group_px = env_int("MVSGI_GROUP_PX", p->interleave ? p->run_len : 32);
   if (p->group_px < 1) p->group_px = 1;
   p->smem_bytes = align_up((int64_t)p->max_pairs * per_pair + (int64_t)p->run_len * 12 + 16, 16);
   p->walk = false;
