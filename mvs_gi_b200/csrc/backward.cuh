@@ -29,7 +29,46 @@ struct SweepBwdKP {
   SweepKP f;             // forward problem (feat = staged features, mbits = packed masks; vol unused)
   const float* gradVol;  // [B, Cout, Dvol, Ho, Wo]
   float* gradStage;      // zero-initialised, staged layout
+  // geometry shared by the frames (fused projection or shared grids): per (candidate, pixel, camera) the tap offset,
+  // frac x, frac y and the mask lookup info, evaluated once by sweep_backward_geom_kernel instead of once per frame
+  // in every quad; nullptr = evaluate in the backward kernel (per-frame grids)
+  const uint4* geom;
 };
+
+// [D][P][CAM] entries: (tap offset incl. the camera's image, frac x, frac y, mask info | kMaskNone)
+template <int CAM, int AGG>
+__global__ void __launch_bounds__(128)
+sweep_backward_geom_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig, uint4* __restrict__ out) {
+  const int pix = blockIdx.x * 128 + threadIdx.x;
+  if (pix >= kp.P) return;
+  const int d = blockIdx.y;
+  const int h = pix / kp.Wo, w = pix - h * kp.Wo;
+  float rx = 0.f, ry = 0.f, rz = 0.f;
+  if (kp.gridMode == MVSGI_GRID_PROJECT) cv_ray(rig, h, w, rx, ry, rz);
+#pragma unroll
+  for (int cam = 0; cam < CAM; ++cam) {
+    float gx, gy;
+    bool gvalid = true;
+    if (kp.gridMode == MVSGI_GRID_PROJECT) {
+      float x, y, z;
+      to_camera(rig.cams[cam], rx, ry, rz, rig.dist[d], x, y, z);
+      gvalid = project(rig.cams[cam], x, y, z, gx, gy);
+    } else {
+      const float2 g = __ldg(reinterpret_cast<const float2*>(kp.grids + cam * kp.gsCam + d * kp.gsD + h * kp.gsY +
+                                                               w * kp.gsX));
+      gx = g.x;
+      gy = g.y;
+      if (AGG == MVSGI_AGG_STD) gvalid = __ldg(kp.gmask + cam * kp.gmCam + d * kp.gmD + h * kp.gmY + w * kp.gmX) != 0;
+    }
+    int off;
+    float lx, ly;
+    make_entry(kp, gx, gy, off, lx, ly);
+    uint32_t info = kMaskNone;
+    if (AGG == MVSGI_AGG_STD && gvalid) info = make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch);
+    out[((long long)d * kp.P + pix) * CAM + cam] =
+        make_uint4((uint32_t)(off + cam * kp.fsCam), __float_as_uint(lx), __float_as_uint(ly), info);
+  }
+}
 
 constexpr int kBwdThreads = 256;  // 64 quads = 64 voxels per block
 
@@ -53,26 +92,35 @@ sweep_backward_kernel(const SweepBwdKP kb, const __grid_constant__ MvsgiRig rig)
   float lx = 0.f, ly = 0.f;
   uint32_t bit = 0;
   if (q < CAM) {
-    float gx, gy;
-    bool gvalid = true;
-    if (kp.gridMode == MVSGI_GRID_PROJECT) {
-      float rx, ry, rz, x, y, z;
-      cv_ray(rig, h, w, rx, ry, rz);
-      to_camera(rig.cams[q], rx, ry, rz, rig.dist[d], x, y, z);
-      gvalid = project(rig.cams[q], x, y, z, gx, gy);
+    uint32_t info = kMaskNone;
+    if (kb.geom != nullptr) {
+      const uint4 e = __ldg(kb.geom + ((long long)d * kp.P + pix) * CAM + q);
+      off = (int)e.x;
+      lx = __uint_as_float(e.y);
+      ly = __uint_as_float(e.z);
+      info = e.w;
     } else {
-      const long long bb = kp.perFrameGrids ? b : 0;
-      const float2 g = __ldg(reinterpret_cast<const float2*>(kp.grids + bb * kp.gsB + q * kp.gsCam + d * kp.gsD +
-                                                               h * kp.gsY + w * kp.gsX));
-      gx = g.x;
-      gy = g.y;
-      if (AGG == MVSGI_AGG_STD)
-        gvalid = __ldg(kp.gmask + bb * kp.gmB + q * kp.gmCam + d * kp.gmD + h * kp.gmY + w * kp.gmX) != 0;
+      float gx, gy;
+      bool gvalid = true;
+      if (kp.gridMode == MVSGI_GRID_PROJECT) {
+        float rx, ry, rz, x, y, z;
+        cv_ray(rig, h, w, rx, ry, rz);
+        to_camera(rig.cams[q], rx, ry, rz, rig.dist[d], x, y, z);
+        gvalid = project(rig.cams[q], x, y, z, gx, gy);
+      } else {
+        const long long bb = kp.perFrameGrids ? b : 0;
+        const float2 g = __ldg(reinterpret_cast<const float2*>(kp.grids + bb * kp.gsB + q * kp.gsCam + d * kp.gsD +
+                                                                 h * kp.gsY + w * kp.gsX));
+        gx = g.x;
+        gy = g.y;
+        if (AGG == MVSGI_AGG_STD)
+          gvalid = __ldg(kp.gmask + bb * kp.gmB + q * kp.gmCam + d * kp.gmD + h * kp.gmY + w * kp.gmX) != 0;
+      }
+      make_entry(kp, gx, gy, off, lx, ly);
+      off += q * kp.fsCam;
+      if (AGG == MVSGI_AGG_STD && gvalid) info = make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch);
     }
-    make_entry(kp, gx, gy, off, lx, ly);
-    off += q * kp.fsCam;
     if (AGG == MVSGI_AGG_STD) {
-      const uint32_t info = gvalid ? make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch) : kMaskNone;
       const uint32_t* mb = kp.mbits + (kp.perFrameMasks ? (long long)b * kp.mbB : 0) + q * kp.mbCam;
       bit = mask_eval(mask_fetch(mb, info, kp.mPitch), info);  // spherical_sweep_avg.py:92-102
     } else {

@@ -358,6 +358,19 @@ int backward_plan(const MvsgiSweepBwdArgs* a, MvsgiSweepArgs* f, SweepPlan* p) {
 }
 
 template <int AGG>
+cudaError_t launch_backward_geom(int cams, const mvsgi::SweepKP& kp, const MvsgiRig& rig, uint4* out, cudaStream_t st) {
+  dim3 grid((kp.P + 127) / 128, kp.D);
+  switch (cams) {
+    case 1: mvsgi::sweep_backward_geom_kernel<1, AGG><<<grid, 128, 0, st>>>(kp, rig, out); break;
+    case 2: mvsgi::sweep_backward_geom_kernel<2, AGG><<<grid, 128, 0, st>>>(kp, rig, out); break;
+    case 3: mvsgi::sweep_backward_geom_kernel<3, AGG><<<grid, 128, 0, st>>>(kp, rig, out); break;
+    default: mvsgi::sweep_backward_geom_kernel<4, AGG><<<grid, 128, 0, st>>>(kp, rig, out); break;
+  }
+  g_launches++;
+  return cudaGetLastError();
+}
+
+template <int AGG>
 cudaError_t launch_sweep_backward(int cams, const mvsgi::SweepBwdKP& kb, const MvsgiRig& rig, cudaStream_t st) {
   const int P = kb.f.P;
   dim3 grid((P + mvsgi::kBwdThreads / 4 - 1) / (mvsgi::kBwdThreads / 4), kb.f.D, kb.f.B);
@@ -538,11 +551,17 @@ int mvsgi_resample_f32(const MvsgiResampleArgs* a, void* stream) {
 
 // ---- backward passes -------------------------------------------------------------------------------------------------
 
+// geometry table of the backward (backward.cuh): only when the geometry is shared by the frames
+static int64_t backward_geom_bytes(const MvsgiSweepArgs& f, const SweepPlan& p) {
+  if (p.per_frame_grids) return 0;
+  return align_up((int64_t)f.num_cands * f.out_h * f.out_w * f.num_cams * 16, 256);
+}
+
 int64_t mvsgi_sweep_backward_workspace_bytes(const MvsgiSweepBwdArgs* a) {
   MvsgiSweepArgs f;
   SweepPlan p;
   const int rc = backward_plan(a, &f, &p);
-  return rc != MVSGI_OK ? (int64_t)rc : p.total_bytes + p.feats_bytes;
+  return rc != MVSGI_OK ? (int64_t)rc : p.total_bytes + p.feats_bytes + backward_geom_bytes(f, p);
 }
 
 int mvsgi_sweep_backward_f32(const MvsgiSweepBwdArgs* a, void* stream) {
@@ -551,7 +570,9 @@ int mvsgi_sweep_backward_f32(const MvsgiSweepBwdArgs* a, void* stream) {
   int rc = backward_plan(a, &f, &p);
   if (rc != MVSGI_OK) return rc;
   if (a->workspace == nullptr) return MVSGI_E_NULL;
-  if (a->workspace_bytes < p.total_bytes + p.feats_bytes || (reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0)
+  const int64_t geom_bytes = backward_geom_bytes(f, p);
+  if (a->workspace_bytes < p.total_bytes + p.feats_bytes + geom_bytes ||
+      (reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0)
     return MVSGI_E_WORKSPACE;
   if (f.batch > 65535 || f.num_cands > 65535 || f.feat_h > 65535) return MVSGI_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -571,9 +592,17 @@ int mvsgi_sweep_backward_f32(const MvsgiSweepBwdArgs* a, void* stream) {
   fill_kp(&f, p, (float*)ws, (uint32_t*)(ws + p.feats_bytes), kb.f);
   kb.gradVol = a->grad_vol;
   kb.gradStage = gstage;
+  kb.geom = nullptr;
   MvsgiRig rig;
   if (f.grid_mode == MVSGI_GRID_PROJECT) rig = *f.rig;
   else memset(&rig, 0, sizeof(rig));
+  if (geom_bytes > 0) {  // geometry once for all frames
+    uint4* geom = (uint4*)(ws + p.total_bytes + p.feats_bytes);
+    e = f.aggregate == MVSGI_AGG_STD ? launch_backward_geom<MVSGI_AGG_STD>(f.num_cams, kb.f, rig, geom, st)
+                                     : launch_backward_geom<MVSGI_AGG_CONCAT>(f.num_cams, kb.f, rig, geom, st);
+    if (e != cudaSuccess) return (int)e;
+    kb.geom = geom;
+  }
   e = f.aggregate == MVSGI_AGG_STD ? launch_sweep_backward<MVSGI_AGG_STD>(f.num_cams, kb, rig, st)
                                    : launch_sweep_backward<MVSGI_AGG_CONCAT>(f.num_cams, kb, rig, st);
   if (e != cudaSuccess) return (int)e;
