@@ -429,6 +429,7 @@ int mvsgi_pack_masks(const void* masks, int32_t dtype, int32_t n_outer, int64_t 
   if (masks == nullptr || bits_out == nullptr) return MVSGI_E_NULL;
   if (n_outer < 1 || n_inner < 1 || mask_h < 1 || mask_w < 1) return MVSGI_E_SHAPE;
   if (dtype != MVSGI_MASK_F32 && dtype != MVSGI_MASK_U8) return MVSGI_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(bits_out) & 7) != 0) return MVSGI_E_STRIDE;  // row pairs are read as 8-byte words
   return (int)launch_pack(masks, dtype, n_outer, stride_outer, n_inner, stride_inner, stride_h, stride_w, mask_h,
                           mask_w, bits_out, flags_out, (cudaStream_t)stream);
 }

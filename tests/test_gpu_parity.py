@@ -444,6 +444,46 @@ def test_cuda_graph_capture_and_replay(dev):
         assert float((gf - got_gf).abs().max()) <= 1e-5 * float(gf.abs().max())
 
 
+def test_pack_masks_public_entry_layout(dev):
+    """mvsgi_pack_masks as a caller of the C ABI sees it: the documented row-pair bit layout, the negative/NaN flag and
+    the alignment check (include/mvsgi_b200.h)."""
+    import ctypes as C
+
+    from mvs_gi_b200 import abi
+
+    lib = abi.load_library()
+    Hm, Wm = 5, 70
+    pitch = int(lib.mvsgi_mask_pitch_words(Wm))
+    gen = np.random.default_rng(12)
+    m = (gen.uniform(0, 1, (2, Hm, Wm)) > 0.5).astype(np.float32)
+    masks = t(m, dev)
+    bits = torch.full((2 * (Hm + 2) * pitch * 2 + 2,), 0x5A5A5A5A, dtype=torch.int32, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def pack(src, out_ptr):
+        return lib.mvsgi_pack_masks(src.data_ptr(), abi.MASK_F32, 2, Hm * Wm, 1, 0, Wm, 1, Hm, Wm, out_ptr,
+                                    flags.data_ptr(), st)
+
+    assert pack(masks, bits.data_ptr()) == 0
+    torch.cuda.synchronize()
+    w = bits.cpu().numpy().view(np.uint32)[:2 * (Hm + 2) * pitch * 2].reshape(2, Hm + 2, pitch, 2)
+    padded = np.zeros((2, Hm + 3, pitch * 32), np.uint8)  # padded rows 0 .. Hm+2, bit 32 + x of a row is pixel x
+    padded[:, 1:Hm + 1, 32:32 + Wm] = m.astype(np.uint8)
+    for n in range(2):
+        for Y in range(Hm + 2):
+            for r in range(2):
+                row_bits = np.unpackbits(w[n, Y, :, r].astype("<u4").view(np.uint8), bitorder="little")
+                assert np.array_equal(row_bits, padded[n, Y + r]), (n, Y, r)
+    assert int(flags.item()) == 0
+    bad = masks.clone()
+    bad[1, 2, 3] = -1.0
+    assert pack(bad, bits.data_ptr()) == 0
+    torch.cuda.synchronize()
+    assert int(flags.item()) & 1
+    assert pack(masks, bits.data_ptr() + 4) == -3  # MVSGI_E_STRIDE: 8-byte alignment
+
+
 def test_candidate_sharded_sweep_two_gpus(dev):
     """NCCL all-gather variant and the fused peer-store variant on 2 GPUs of one box (skipped on a 1-GPU box)."""
     import json
