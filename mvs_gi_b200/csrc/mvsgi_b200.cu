@@ -124,9 +124,9 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
 
   // Work decomposition (sweep.cuh): equal runs of output pixels, one per resident CTA when the tap table fits.
   const int P = a->out_h * a->out_w;
-  int ctas_per_sm = env_int("MVSGI_CTAS_PER_SM", 2);
+  int ctas_per_sm = env_int("MVSGI_CTAS_PER_SM", mvsgi::kSweepCtas);
   if (ctas_per_sm < 1) ctas_per_sm = 1;
-  if (ctas_per_sm > 2) ctas_per_sm = 2;  // __launch_bounds__(512, 2)
+  if (ctas_per_sm > mvsgi::kSweepCtas) ctas_per_sm = mvsgi::kSweepCtas;  // __launch_bounds__
   const int grid_target = device_sms() * ctas_per_sm;
   int dch = env_int("MVSGI_DCH", 16);
   if (dch < 1) dch = 1;
@@ -134,7 +134,7 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   const bool std_tab = std_agg;
   const int64_t per_pair = (int64_t)mvsgi::entry_words(a->num_cams) * 4 + (std_tab ? a->num_cams * 4 : 0);
   const int64_t per_px = (int64_t)dch * per_pair + 12;
-  const int64_t budget = env_int("MVSGI_TABLE_BYTES", ctas_per_sm == 2 ? 80 * 1024 : 160 * 1024);
+  const int64_t budget = env_int("MVSGI_TABLE_BYTES", ctas_per_sm >= 4 ? 48 * 1024 : (ctas_per_sm == 2 ? 80 * 1024 : 160 * 1024));
   const int num_oct = (P + 7) / 8;
   int run_oct = (num_oct + grid_target - 1) / grid_target;
   if ((int64_t)run_oct * 8 * per_px > budget) run_oct = (int)(budget / (8 * per_px));

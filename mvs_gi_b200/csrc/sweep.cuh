@@ -34,7 +34,13 @@
 namespace mvsgi {
 
 constexpr int kCG = 16;             // channels per staged channel group
+#ifdef MVSGI_SWEEP_THREADS
+constexpr int kSweepThreads = MVSGI_SWEEP_THREADS;
+constexpr int kSweepCtas = 1024 / MVSGI_SWEEP_THREADS;
+#else
 constexpr int kSweepThreads = 512;  // 128 quads per CTA
+constexpr int kSweepCtas = 2;
+#endif
 constexpr uint32_t kMaskNone = 0u;
 
 struct SweepKP {
@@ -170,7 +176,7 @@ MVSGI_DEV void make_entry(const SweepKP& kp, float gx, float gy, int& off, float
 __host__ __device__ constexpr int entry_words(int cam) { return (2 + 3 * cam) | 1; }
 
 template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16>
-__global__ void __launch_bounds__(kSweepThreads, 2)
+__global__ void __launch_bounds__(kSweepThreads, kSweepCtas)
 sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int ES = entry_words(CAM);
