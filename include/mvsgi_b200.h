@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MVSGI_ABI_VERSION 7
+#define MVSGI_ABI_VERSION 8
 #define MVSGI_MAX_CAMS 4
 #define MVSGI_MAX_CANDS 64
 #define MVSGI_MAX_PEERS 7 /* extra destinations of a candidate-sharded sweep (8 GPUs of one box) */
@@ -71,6 +71,10 @@ enum { MVSGI_MASK_F32 = 0, MVSGI_MASK_U8 = 1 };
  * common_modules.py:82-115) consumes without a transpose.  Needs feat_chs % 4 == 0 and 16-byte aligned volumes.
  * SURVEY.md §8 row f2. */
 #define MVSGI_FLAG_VOL_CHANNELS_LAST 8u
+/* Use the CTA-resident-table sweep kernel (sweep.cuh) even where the tile-pipelined one (sweep_tiled.cuh, the default
+ * whenever the geometry is shared by all frames and the features are staged as fp32) applies.  Both kernels produce
+ * bit-identical volumes; the flag exists so that tests and bench.py can hold one against the other. */
+#define MVSGI_FLAG_CTA_TABLE 16u
 
 /* ---- calibration ------------------------------------------------------- */
 /* One camera the sweep projects into.  rot/trans are the INVERSE pose

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_CAMS = 4
 MAX_CANDS = 64
 MAX_PEERS = 7
@@ -24,6 +24,7 @@ FLAG_FEATS_BF16 = 1
 FLAG_STAGE_ONLY = 2
 FLAG_SWEEP_ONLY = 4
 FLAG_VOL_CHANNELS_LAST = 8
+FLAG_CTA_TABLE = 16
 RESAMPLE_IMG_U8 = 1
 
 LIB_NAME = "libmvsgi_b200.so"

@@ -1,0 +1,39 @@
+// launch.h — internal interface between the translation units of libmvsgi_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "sweep_tiled.cuh"
+
+namespace mvsgi {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize only ever has to grow, and is per device: remember what was set
+constexpr int kMaxDevices = 32;
+struct DynSmemSet {
+  size_t bytes[kMaxDevices] = {};
+};
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kern, size_t smem, DynSmemSet& set) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < kMaxDevices && smem <= set.bytes[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && dev >= 0 && dev < kMaxDevices) set.bytes[dev] = smem;
+  return e;
+}
+
+// sweep_cta.cu: the CTA-resident-table sweep (sweep.cuh) — per-frame grids, bf16-staged features, any shape
+cudaError_t launch_sweep_cta(int aggregate, int cams, const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
+                             cudaStream_t st);
+#ifdef MVSGI_EXPERIMENTS
+cudaError_t launch_sweep_walk(int aggregate, int cams, const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
+                              cudaStream_t st);
+#endif
+
+// sweep_tiled.cu: geometry table + tile-pipelined sweep (sweep_tiled.cuh); 2 launches
+cudaError_t launch_tile_table(int aggregate, int cams, const SweepKP& kp, const TiledKP& tp, const MvsgiRig& rig,
+                              cudaStream_t st);
+cudaError_t launch_sweep_tiled(int aggregate, int cams, const SweepKP& kp, const TiledKP& tp, int grid, size_t smem,
+                               cudaStream_t st);
+
+}  // namespace mvsgi

@@ -7,10 +7,37 @@
 
 #include "softargmin.cuh"
 #include "stage.cuh"
-#include "sweep.cuh"
+#include "launch.h"
+#ifdef MVSGI_EXPERIMENTS
 #include "sweep_walk.cuh"
+#endif
 #include "backward.cuh"
 #include "resample.cuh"
+
+namespace mvsgi {
+
+// ---- grid dump (mvsgi_project_only_f32): exactly the (gx, gy, valid) the build step computes -----------------------
+__global__ void project_only_kernel(const __grid_constant__ MvsgiRig rig, float* __restrict__ grids,
+                                    uint8_t* __restrict__ gmask) {
+  const int Ho = rig.cv_height, Wo = rig.cv_width;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Ho * Wo) return;
+  const int h = idx / Wo, w = idx % Wo;
+  float rx, ry, rz;
+  cv_ray(rig, h, w, rx, ry, rz);
+  for (int cam = 0; cam < rig.num_cams; ++cam)
+    for (int d = 0; d < rig.num_cands; ++d) {
+      float x, y, z, gx, gy;
+      to_camera(rig.cams[cam], rx, ry, rz, rig.dist[d], x, y, z);
+      const bool valid = project(rig.cams[cam], x, y, z, gx, gy);
+      const long long o = ((long long)(cam * rig.num_cands + d) * Ho + h) * Wo + w;
+      grids[o * 2] = gx;
+      grids[o * 2 + 1] = gy;
+      gmask[o] = valid ? 1 : 0;
+    }
+}
+
+}  // namespace mvsgi
 
 namespace {
 
@@ -18,10 +45,16 @@ std::atomic<long long> g_launches{0};
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+// Planner knobs are compile-time constants in the shipped library; `make exp` (-DMVSGI_EXPERIMENTS) lets the
+// environment override them for tuning runs.
+#ifdef MVSGI_EXPERIMENTS
 int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;
 }
+#else
+constexpr int env_int(const char*, int dflt) { return dflt; }
+#endif
 
 struct SweepPlan {
   bool pack_masks;        // std builder: masks -> bit images
@@ -34,16 +67,25 @@ struct SweepPlan {
   int dch, num_chunks, num_runs, run_len, num_items, max_pairs, grid, group_px, interleave;
   size_t smem_bytes;
   int cout;
-  bool walk;              // channels-last volume: sweep_walk.cuh
+  bool walk;              // channels-last volume: sweep_walk.cuh (experiment builds only)
   int w_len, w_segs, w_num_seg;
+  // tile-pipelined sweep (sweep_tiled.cuh)
+  bool tiled;
+  int tile_h, oct_per_row, tiles_x, num_tiles, steps_per_item, items_per_tile, tiled_items;
+  int chunk_bytes, minfo_off, vinfo_off, tiled_grid;
+  int64_t table_bytes;
+  size_t tiled_smem;
 };
 
 int mask_pitch_words(int mask_w) { return (mask_w + 31) / 32 + 2; }  // zero guard word + data words + zero guard
 
 int device_sms() {
+  static int cached[mvsgi::kMaxDevices] = {};  // 0 = not asked yet
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < mvsgi::kMaxDevices && cached[dev] > 0) return cached[dev];
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+  if (dev >= 0 && dev < mvsgi::kMaxDevices) cached[dev] = sms;
   return sms;
 }
 
@@ -52,7 +94,8 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   if (a->struct_size != sizeof(MvsgiSweepArgs)) return MVSGI_E_VERSION;
   if (a->aggregate != MVSGI_AGG_STD && a->aggregate != MVSGI_AGG_CONCAT) return MVSGI_E_UNSUPPORTED;
   if (a->grid_mode != MVSGI_GRID_SUPPLIED && a->grid_mode != MVSGI_GRID_PROJECT) return MVSGI_E_UNSUPPORTED;
-  if (a->flags & ~(MVSGI_FLAG_FEATS_BF16 | MVSGI_FLAG_STAGE_ONLY | MVSGI_FLAG_SWEEP_ONLY | MVSGI_FLAG_VOL_CHANNELS_LAST))
+  if (a->flags & ~(MVSGI_FLAG_FEATS_BF16 | MVSGI_FLAG_STAGE_ONLY | MVSGI_FLAG_SWEEP_ONLY | MVSGI_FLAG_VOL_CHANNELS_LAST |
+                   MVSGI_FLAG_CTA_TABLE))
     return MVSGI_E_UNSUPPORTED;
   if ((a->flags & MVSGI_FLAG_STAGE_ONLY) && (a->flags & MVSGI_FLAG_SWEEP_ONLY)) return MVSGI_E_UNSUPPORTED;
   // bf16 staging is a plain-forward mode: no validity output, no peer stores
@@ -159,6 +202,7 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   // walking quads.  One 512-thread CTA per SM; a run is w_segs segments of
   // w_len consecutive pixels taken round-robin over the image; task = (segment, candidate), one per quad when
   // w_segs * dch == 128.
+#ifdef MVSGI_EXPERIMENTS
   if ((a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) && !(a->flags & MVSGI_FLAG_FEATS_BF16) && a->num_cams >= 3 &&
       env_int("MVSGI_WALK", 0)) {
     const int sms = device_sms();
@@ -181,6 +225,37 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
       p->grid = p->num_items < sms ? p->num_items : sms;
       p->smem_bytes = align_up((int64_t)p->max_pairs * per_pair + (int64_t)p->run_len * 12 + 16, 16);
     }
+  }
+#endif
+
+  // Tile-pipelined sweep (sweep_tiled.cuh): whenever the geometry is shared by the frames and the features are staged
+  // as fp32.  Tile = 8 rows x 16 pixels; one chunk of the geometry table per (tile, candidate).
+  p->tiled = !p->per_frame_grids && !(a->flags & (MVSGI_FLAG_FEATS_BF16 | MVSGI_FLAG_CTA_TABLE)) && !p->walk &&
+             env_int("MVSGI_TILED", 1) != 0;
+  p->table_bytes = 0;
+  if (p->tiled) {
+    p->tile_h = env_int("MVSGI_TILE_H", 8);
+    if (p->tile_h != 16 && p->tile_h != 8 && p->tile_h != 4 && p->tile_h != 2 && p->tile_h != 1) p->tile_h = 8;
+    p->oct_per_row = mvsgi::kTileWarps / p->tile_h;
+    p->tiles_x = (a->out_w + p->oct_per_row * 8 - 1) / (p->oct_per_row * 8);
+    p->num_tiles = p->tiles_x * ((a->out_h + p->tile_h - 1) / p->tile_h);
+    const int rec_bytes = a->num_cams * mvsgi::kTileVox * 16;
+    p->minfo_off = rec_bytes;
+    p->vinfo_off = rec_bytes + (p->per_frame_masks ? mvsgi::kTileVox * 16 : 0);
+    p->chunk_bytes = p->vinfo_off + mvsgi::kTileVox * 4;
+    // enough items to keep every CTA busy and the tail short: split the candidates of a tile when frames x tiles is small
+    const int64_t want = 8ll * grid_target;
+    int ipt = 1;
+    while ((int64_t)a->batch * p->num_tiles * ipt < want && ipt * 2 <= a->num_cands) ipt *= 2;
+    p->steps_per_item = (a->num_cands + ipt - 1) / ipt;
+    p->items_per_tile = (a->num_cands + p->steps_per_item - 1) / p->steps_per_item;
+    const int64_t items = (int64_t)a->batch * p->num_tiles * p->items_per_tile;
+    if (items >= (1ll << 30)) return MVSGI_E_SHAPE;
+    p->tiled_items = (int)items;
+    p->tiled_grid = (int)(items < grid_target ? items : grid_target);
+    p->table_bytes = align_up((int64_t)p->num_tiles * a->num_cands * p->chunk_bytes, 256);
+    p->tiled_smem = (size_t)mvsgi::kTileStages * p->chunk_bytes + mvsgi::kTileStages * (8 + 8 + 16 + 16);
+    p->total_bytes += p->table_bytes;
   }
   return MVSGI_OK;
 }
@@ -230,77 +305,6 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   for (int i = 0; i < a->num_peers; ++i) kp.peerDelta[i] = (long long)((reinterpret_cast<intptr_t>(a->peer_vols[i]) - reinterpret_cast<intptr_t>(a->vol)) / 4);
 }
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16 = false>
-cudaError_t launch_sweep_cl(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
-  auto kern = mvsgi::sweep_kernel<CAM, AGG, FULLC, VALID, PEERS, CL, BF16>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, mvsgi::kSweepThreads, smem, st>>>(kp, rig);
-  g_launches++;
-  return cudaGetLastError();
-}
-
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS = false>
-cudaError_t launch_sweep(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
-  return kp.volChannelsLast ? launch_sweep_cl<CAM, AGG, FULLC, VALID, PEERS, true>(kp, rig, grid, smem, st)
-                            : launch_sweep_cl<CAM, AGG, FULLC, VALID, PEERS, false>(kp, rig, grid, smem, st);
-}
-
-template <int CAM, int AGG>
-cudaError_t dispatch_flags(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
-  const bool fullc = kp.C % mvsgi::kCG == 0;
-  const bool valid = kp.validOut != nullptr;
-  if (kp.featsBf16) {  // validate_and_plan: no validity output, no peers in this mode
-    if (kp.volChannelsLast)
-      return fullc ? launch_sweep_cl<CAM, AGG, true, false, false, true, true>(kp, rig, grid, smem, st)
-                   : launch_sweep_cl<CAM, AGG, false, false, false, true, true>(kp, rig, grid, smem, st);
-    return fullc ? launch_sweep_cl<CAM, AGG, true, false, false, false, true>(kp, rig, grid, smem, st)
-                 : launch_sweep_cl<CAM, AGG, false, false, false, false, true>(kp, rig, grid, smem, st);
-  }
-  if (kp.numPeers > 0)
-    return fullc ? launch_sweep<CAM, AGG, true, false, true>(kp, rig, grid, smem, st)
-                 : launch_sweep<CAM, AGG, false, false, true>(kp, rig, grid, smem, st);
-  if (AGG == MVSGI_AGG_STD && valid)
-    return fullc ? launch_sweep<CAM, AGG, true, true>(kp, rig, grid, smem, st)
-                 : launch_sweep<CAM, AGG, false, true>(kp, rig, grid, smem, st);
-  return fullc ? launch_sweep<CAM, AGG, true, false>(kp, rig, grid, smem, st)
-               : launch_sweep<CAM, AGG, false, false>(kp, rig, grid, smem, st);
-}
-
-template <int CAM, int AGG, bool VALID, bool PEERS>
-cudaError_t launch_walk(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
-  auto kern = mvsgi::sweep_walk_kernel<CAM, AGG, VALID, PEERS>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, mvsgi::kWalkThreads, smem, st>>>(kp, rig);
-  g_launches++;
-  return cudaGetLastError();
-}
-
-template <int CAM, int AGG>
-cudaError_t dispatch_walk(const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
-  if (kp.numPeers > 0) return launch_walk<CAM, AGG, false, true>(kp, rig, grid, smem, st);
-  if (AGG == MVSGI_AGG_STD && kp.validOut != nullptr) return launch_walk<CAM, AGG, true, false>(kp, rig, grid, smem, st);
-  return launch_walk<CAM, AGG, false, false>(kp, rig, grid, smem, st);
-}
-
-template <int AGG>
-cudaError_t dispatch_cams(int cams, const mvsgi::SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
-                          cudaStream_t st) {
-  if (kp.wL > 0) {
-    switch (cams) {
-      case 3: return dispatch_walk<3, AGG>(kp, rig, grid, smem, st);
-      default: return dispatch_walk<4, AGG>(kp, rig, grid, smem, st);
-    }
-  }
-  switch (cams) {
-    case 1: return dispatch_flags<1, AGG>(kp, rig, grid, smem, st);
-    case 2: return dispatch_flags<2, AGG>(kp, rig, grid, smem, st);
-    case 3: return dispatch_flags<3, AGG>(kp, rig, grid, smem, st);
-    default: return dispatch_flags<4, AGG>(kp, rig, grid, smem, st);
-  }
-}
-
 cudaError_t launch_pack(const void* masks, int dtype, int n0, int64_t s0, int n1, int64_t s1, int64_t sh, int64_t sw,
                         int Hm, int Wm, uint32_t* bits, int* flags, cudaStream_t st) {
   const int pitch = mask_pitch_words(Wm);
@@ -339,6 +343,13 @@ void launch_softargmin_x2(const mvsgi::SoftKP& kp, dim3 grid, cudaStream_t st) {
   else launch_x2_flags<16, false>(kp, grid, st);
 }
 
+void fill_tp(const SweepPlan& p, unsigned char* table, int* queue, mvsgi::TiledKP& tp) {
+  tp.tileH = p.tile_h; tp.octPerRow = p.oct_per_row; tp.tilesX = p.tiles_x; tp.numTiles = p.num_tiles;
+  tp.stepsPerItem = p.steps_per_item; tp.itemsPerTile = p.items_per_tile; tp.numItems = p.tiled_items;
+  tp.chunkBytes = p.chunk_bytes; tp.minfoOff = p.minfo_off; tp.vinfoOff = p.vinfo_off;
+  tp.table = table; tp.queue = queue;
+}
+
 }  // namespace
 
 namespace {
@@ -353,7 +364,7 @@ int backward_plan(const MvsgiSweepBwdArgs* a, MvsgiSweepArgs* f, SweepPlan* p) {
   f->vol = const_cast<float*>(a->grad_vol);  // only has to be non-NULL for validation; never written
   f->valid_out = nullptr;
   f->num_peers = 0;
-  f->flags = 0;
+  f->flags = MVSGI_FLAG_CTA_TABLE;  // the backward only uses the staging part of the plan: no geometry table in its workspace
   return validate_and_plan(f, p);
 }
 
@@ -419,8 +430,9 @@ int mvsgi_sweep_launch_count(const MvsgiSweepArgs* a) {
   if (rc != MVSGI_OK) return rc;
   const int stage = 1 + (p.pack_masks ? 1 : 0);
   if (a->flags & MVSGI_FLAG_STAGE_ONLY) return stage;
-  if (a->flags & MVSGI_FLAG_SWEEP_ONLY) return 1;
-  return 1 + stage;
+  const int sweep = p.tiled ? 2 : 1;  // geometry table + sweep
+  if (a->flags & MVSGI_FLAG_SWEEP_ONLY) return sweep;
+  return sweep + stage;
 }
 
 int mvsgi_pack_masks(const void* masks, int32_t dtype, int32_t n_outer, int64_t stride_outer, int32_t n_inner,
@@ -446,7 +458,6 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
   float* ws_feats = (float*)ws;
   uint32_t* ws_bits = (uint32_t*)(ws + p.feats_bytes);
   int* ws_flags = (int*)(ws + p.feats_bytes + p.mask_bytes);
-  const bool std_agg = a->aggregate == MVSGI_AGG_STD;
   const bool do_stage = !(a->flags & MVSGI_FLAG_SWEEP_ONLY);
   const bool do_sweep = !(a->flags & MVSGI_FLAG_STAGE_ONLY);
   const int Wp = a->feat_w + 2, Hp1 = a->feat_h + 3;
@@ -475,7 +486,9 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
 
   // 2. masks -> bits
   if (p.pack_masks && do_stage) {
-    cudaError_t e = launch_pack(a->masks, a->masks_dtype, p.per_frame_masks ? a->batch : 1, a->masks_stride[0],
+    cudaError_t e = cudaMemsetAsync(ws_flags, 0, sizeof(int), st);  // bit 0: a mask value was negative or NaN
+    if (e != cudaSuccess) return (int)e;
+    e = launch_pack(a->masks, a->masks_dtype, p.per_frame_masks ? a->batch : 1, a->masks_stride[0],
                                 a->num_cams, a->masks_stride[1], a->masks_stride[2], a->masks_stride[3], a->mask_h,
                                 a->mask_w, ws_bits, ws_flags, st);
     if (e != cudaSuccess) return (int)e;
@@ -490,8 +503,30 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
   if (a->grid_mode == MVSGI_GRID_PROJECT) rig = *a->rig;
   else memset(&rig, 0, sizeof(rig));
 
-  cudaError_t e = std_agg ? dispatch_cams<MVSGI_AGG_STD>(a->num_cams, kp, rig, p.grid, p.smem_bytes, st)
-                          : dispatch_cams<MVSGI_AGG_CONCAT>(a->num_cams, kp, rig, p.grid, p.smem_bytes, st);
+  cudaError_t e;
+  if (p.tiled) {
+    // geometry table (once per call, shared by all frames), then the item queue counter, then the sweep
+    int* queue = ws_flags + 32;
+    mvsgi::TiledKP tp;
+    fill_tp(p, (unsigned char*)(ws + p.feats_bytes + p.mask_bytes + p.flag_bytes), queue, tp);
+    e = mvsgi::launch_tile_table(a->aggregate, a->num_cams, kp, tp, rig, st);
+    if (e != cudaSuccess) return (int)e;
+    g_launches++;
+    e = cudaMemsetAsync(queue, 0, sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    e = mvsgi::launch_sweep_tiled(a->aggregate, a->num_cams, kp, tp, p.tiled_grid, p.tiled_smem, st);
+    g_launches++;
+    return (int)e;
+  }
+#ifdef MVSGI_EXPERIMENTS
+  if (p.walk) {
+    e = mvsgi::launch_sweep_walk(a->aggregate, a->num_cams, kp, rig, p.grid, p.smem_bytes, st);
+    g_launches++;
+    return (int)e;
+  }
+#endif
+  e = mvsgi::launch_sweep_cta(a->aggregate, a->num_cams, kp, rig, p.grid, p.smem_bytes, st);
+  g_launches++;
   return (int)e;
 }
 
@@ -711,9 +746,8 @@ int mvsgi_softargmin_f32(const MvsgiSoftArgminArgs* a, void* stream) {
   } else {
     int split = a->num_cands <= 16 ? 1 : (a->num_cands <= 32 ? 2 : 4);
     const int forced = env_int("MVSGI_SOFTARGMIN_DSPLIT", 0);
-    if (forced == 1 || forced == 2 || forced == 4) {
-      if ((a->num_cands + forced - 1) / forced <= 16) split = forced;
-    }
+    if ((forced == 1 || forced == 2 || forced == 4) && (a->num_cands + (forced > 0 ? forced : 1) - 1) / (forced > 0 ? forced : 1) <= 16)
+      split = forced;
     const int ppb = 4 * (32 / split);  // output pixels per 128-thread block
     dim3 grid((a->out_w + ppb - 1) / ppb, a->out_h, a->batch);
     if (split == 1) mvsgi::softargmin_kernel<1><<<grid, 128, 0, st>>>(kp);

@@ -411,25 +411,4 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   }
 }
 
-// ---- grid dump (mvsgi_project_only_f32): exactly the (gx, gy, valid) the build step computes -----------------------
-__global__ void project_only_kernel(const __grid_constant__ MvsgiRig rig, float* __restrict__ grids,
-                                    uint8_t* __restrict__ gmask) {
-  const int Ho = rig.cv_height, Wo = rig.cv_width;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Ho * Wo) return;
-  const int h = idx / Wo, w = idx % Wo;
-  float rx, ry, rz;
-  cv_ray(rig, h, w, rx, ry, rz);
-  for (int cam = 0; cam < rig.num_cams; ++cam)
-    for (int d = 0; d < rig.num_cands; ++d) {
-      float x, y, z, gx, gy;
-      to_camera(rig.cams[cam], rx, ry, rz, rig.dist[d], x, y, z);
-      const bool valid = project(rig.cams[cam], x, y, z, gx, gy);
-      const long long o = ((long long)(cam * rig.num_cands + d) * Ho + h) * Wo + w;
-      grids[o * 2] = gx;
-      grids[o * 2 + 1] = gy;
-      gmask[o] = valid ? 1 : 0;
-    }
-}
-
 }  // namespace mvsgi
