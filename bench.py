@@ -44,8 +44,6 @@ def parse():
     ap.add_argument("--vol-layout", default="ndhwc", choices=["ncdhw", "ndhwc"],
                     help="memory layout of the cost volume: ncdhw = the reference's; ndhwc = channels_last_3d strides "
                          "(MVSGI_FLAG_VOL_CHANNELS_LAST, what cuDNN's NDHWC Conv3d of post_vol consumes)")
-    ap.add_argument("--kernel", default="tiled", choices=["tiled", "cta"],
-                    help="tiled = tile-pipelined sweep (default); cta = the CTA-resident-table kernel (MVSGI_FLAG_CTA_TABLE)")
     ap.add_argument("--norm-costs", action="store_true", help="also write norm_costs (training consumers)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the other-layout / bf16-staging kernel timings")
@@ -231,7 +229,7 @@ def run_b200(args, w):
         if args.feats_layout == "nhwc":
             f = f.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
         calls.append(ops.SweepCall(f, None, None, masks, rig_blob, agg, w.cv_hw[0], w.cv_hw[1], w.num_cands,
-                                   channels_last=args.vol_layout == "ndhwc", cta_table=args.kernel == "cta"))
+                                   channels_last=args.vol_layout == "ndhwc"))
         costs_sets.append(torch.randn((B, 1, w.num_cands, *w.cv_hw), device=dev, generator=gen))
     reg = modules.DistanceRegressorWithFixedCandidates(w.bf, w.dist_list, w.scale, True).to(dev)
     Ho, Wo, scale = reg._out_size(*w.cv_hw)

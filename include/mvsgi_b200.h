@@ -71,10 +71,16 @@ enum { MVSGI_MASK_F32 = 0, MVSGI_MASK_U8 = 1 };
  * common_modules.py:82-115) consumes without a transpose.  Needs feat_chs % 4 == 0 and 16-byte aligned volumes.
  * SURVEY.md §8 row f2. */
 #define MVSGI_FLAG_VOL_CHANNELS_LAST 8u
-/* Use the CTA-resident-table sweep kernel (sweep.cuh) even where the tile-pipelined one (sweep_tiled.cuh, the default
- * whenever the geometry is shared by all frames and the features are staged as fp32) applies.  Both kernels produce
+/* Use the CTA-resident-table sweep kernel (sweep.cuh) even where the tile-walking one (sweep_tiled.cuh, the default
+ * whenever the geometry is shared by all frames and the features are fp32) applies.  Both kernels produce
  * bit-identical volumes; the flag exists so that tests and bench.py can hold one against the other. */
 #define MVSGI_FLAG_CTA_TABLE 16u
+/* Stage the features into the zero-framed workspace copy even when they could be tapped where they are.  Features
+ * are tapped in place (no staging pass, no workspace for them) when they are channels-last — feats_stride[2] == 1 —
+ * with feat_chs a multiple of 16, the other strides multiples of 16 elements and a 128-byte aligned base; any other
+ * layout (NCHW from cuDNN, odd channel counts) is transposed into the staged copy first.  Same volume bits either way
+ * for finite features; the flag exists for tests and bench.py. */
+#define MVSGI_FLAG_STAGED_FEATS 32u
 
 /* ---- calibration ------------------------------------------------------- */
 /* One camera the sweep projects into.  rot/trans are the INVERSE pose
@@ -170,7 +176,8 @@ typedef struct MvsgiSweepArgs {
 } MvsgiSweepArgs;
 
 /* Scratch the sweep needs for this problem (channels-last staging of feats when
- * they are not already channels-last, bit-packed masks).  Negative = error. */
+ * they are not already channels-last — see MVSGI_FLAG_STAGED_FEATS —, bit-packed masks,
+ * the per-launch geometry table).  Negative = error. */
 int64_t mvsgi_sweep_workspace_bytes(const MvsgiSweepArgs* args);
 
 /* Enqueue staging (if needed) + the fused sweep/aggregate kernel. */

@@ -25,6 +25,7 @@ FLAG_STAGE_ONLY = 2
 FLAG_SWEEP_ONLY = 4
 FLAG_VOL_CHANNELS_LAST = 8
 FLAG_CTA_TABLE = 16
+FLAG_STAGED_FEATS = 32
 RESAMPLE_IMG_U8 = 1
 
 LIB_NAME = "libmvsgi_b200.so"

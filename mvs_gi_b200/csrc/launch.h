@@ -2,7 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "sweep.cuh"
+#ifdef MVSGI_EXPERIMENTS
 #include "sweep_tiled.cuh"
+#endif
 
 namespace mvsgi {
 
@@ -30,10 +33,15 @@ cudaError_t launch_sweep_walk(int aggregate, int cams, const SweepKP& kp, const 
                               cudaStream_t st);
 #endif
 
-// sweep_tiled.cu: geometry table + tile-pipelined sweep (sweep_tiled.cuh); 2 launches
+#ifdef MVSGI_EXPERIMENTS
+// sweep_tiled.cu: shape of the tile-walking kernel (compile-time constants of that translation unit)
+int tiled_warps_per_cta();
+int tiled_ctas_per_sm();
+// sweep_tiled.cu: geometry table + tile-walking sweep (sweep_tiled.cuh); 2 launches
 cudaError_t launch_tile_table(int aggregate, int cams, const SweepKP& kp, const TiledKP& tp, const MvsgiRig& rig,
                               cudaStream_t st);
-cudaError_t launch_sweep_tiled(int aggregate, int cams, const SweepKP& kp, const TiledKP& tp, int grid, size_t smem,
+cudaError_t launch_sweep_tiled(int aggregate, int cams, const SweepKP& kp, const TiledKP& tp, int grid, int frames_per_pass,
                                cudaStream_t st);
+#endif
 
 }  // namespace mvsgi

@@ -69,12 +69,13 @@ struct SweepPlan {
   int cout;
   bool walk;              // channels-last volume: sweep_walk.cuh (experiment builds only)
   int w_len, w_segs, w_num_seg;
-  // tile-pipelined sweep (sweep_tiled.cuh)
+  // tile-walking sweep (sweep_tiled.cuh)
   bool tiled;
+  bool direct;            // features are tapped in the caller's channels-last tensor: nothing is staged
+  int frames_per_pass, frame_groups;
   int tile_h, oct_per_row, tiles_x, num_tiles, steps_per_item, items_per_tile, tiled_items;
   int chunk_bytes, minfo_off, vinfo_off, tiled_grid;
   int64_t table_bytes;
-  size_t tiled_smem;
 };
 
 int mask_pitch_words(int mask_w) { return (mask_w + 31) / 32 + 2; }  // zero guard word + data words + zero guard
@@ -95,7 +96,7 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   if (a->aggregate != MVSGI_AGG_STD && a->aggregate != MVSGI_AGG_CONCAT) return MVSGI_E_UNSUPPORTED;
   if (a->grid_mode != MVSGI_GRID_SUPPLIED && a->grid_mode != MVSGI_GRID_PROJECT) return MVSGI_E_UNSUPPORTED;
   if (a->flags & ~(MVSGI_FLAG_FEATS_BF16 | MVSGI_FLAG_STAGE_ONLY | MVSGI_FLAG_SWEEP_ONLY | MVSGI_FLAG_VOL_CHANNELS_LAST |
-                   MVSGI_FLAG_CTA_TABLE))
+                   MVSGI_FLAG_CTA_TABLE | MVSGI_FLAG_STAGED_FEATS))
     return MVSGI_E_UNSUPPORTED;
   if ((a->flags & MVSGI_FLAG_STAGE_ONLY) && (a->flags & MVSGI_FLAG_SWEEP_ONLY)) return MVSGI_E_UNSUPPORTED;
   // bf16 staging is a plain-forward mode: no validity output, no peer stores
@@ -108,6 +109,8 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   // in-image tap offsets and in-frame output offsets are kept in int32
   const int64_t cg64 = (a->feat_chs + mvsgi::kCG - 1) / mvsgi::kCG;
   if ((int64_t)a->num_cams * cg64 * (a->feat_h + 3) * (a->feat_w + 2) * mvsgi::kCG >= (1ll << 31)) return MVSGI_E_SHAPE;
+  for (int i = 0; i < 5; ++i)
+    if (a->feats_stride[i] < 0) return MVSGI_E_STRIDE;
   const int64_t cout64 = (int64_t)a->feat_chs * (a->aggregate == MVSGI_AGG_CONCAT ? a->num_cams : 1);
   // candidate-sharded call: this call's candidates are a slice of the volume's
   if (a->vol_num_cands < 0 || a->cand_offset < 0 || a->num_peers < 0 || a->num_peers > MVSGI_MAX_PEERS) return MVSGI_E_SHAPE;
@@ -159,8 +162,29 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   p->n_mask_images = std_agg ? (p->per_frame_masks ? a->batch : 1) * a->num_cams : 0;
   p->mask_pitch = std_agg ? mask_pitch_words(a->mask_w) : 0;
   p->mask_words = std_agg ? (a->mask_h + 2) * p->mask_pitch * 2 : 0;  // row pairs, each row stored twice (stage.cuh)
-  p->feats_bytes = align_up((int64_t)a->batch * a->num_cams * p->cg * (a->feat_h + 3) * (a->feat_w + 2) * mvsgi::kCG *
-                                ((a->flags & MVSGI_FLAG_FEATS_BF16) ? 2 : 4), 256);
+  // Tile-walking sweep (sweep_tiled.cuh): experiment builds only (MVSGI_TILED=1), measured slower than the CTA-table
+  // kernel on every BASELINE.json shape but the 4-camera one.
+#ifdef MVSGI_EXPERIMENTS
+  p->tiled = !p->per_frame_grids && !(a->flags & (MVSGI_FLAG_FEATS_BF16 | MVSGI_FLAG_CTA_TABLE)) &&
+             env_int("MVSGI_TILED", 0) != 0 && env_int("MVSGI_WALK", 0) == 0;
+#else
+  p->tiled = false;
+#endif
+  // Channels-last features with whole 16-channel groups (north_star (a)) are tapped where they are: the table records
+  // carry clamped offsets and edge flags instead of relying on a zero frame (sweep_tiled.cuh, make_record).
+  {
+    const int64_t* fs = a->feats_stride;
+    const int64_t span = (int64_t)(a->num_cams - 1) * fs[1] + (int64_t)(a->feat_h - 1) * fs[3] +
+                         (int64_t)(a->feat_w - 1) * fs[4] + a->feat_chs;
+    p->direct = !(a->flags & (MVSGI_FLAG_STAGED_FEATS | MVSGI_FLAG_FEATS_BF16)) && fs[2] == 1 &&
+                a->feat_chs % mvsgi::kCG == 0 && fs[4] >= a->feat_chs && fs[0] % 16 == 0 && fs[1] % 16 == 0 &&
+                fs[3] % 16 == 0 && fs[4] % 16 == 0 && span < (1ll << 31) &&
+                (reinterpret_cast<uintptr_t>(a->feats) & 127) == 0 && env_int("MVSGI_DIRECT", 1) != 0 &&
+                env_int("MVSGI_WALK", 0) == 0;
+  }
+  p->feats_bytes = p->direct ? 0
+                             : align_up((int64_t)a->batch * a->num_cams * p->cg * (a->feat_h + 3) * (a->feat_w + 2) *
+                                            mvsgi::kCG * ((a->flags & MVSGI_FLAG_FEATS_BF16) ? 2 : 4), 256);
   p->mask_bytes = align_up((int64_t)p->n_mask_images * p->mask_words * 4 + 16, 256);  // +16: funnel-shift over-read
   p->flag_bytes = 256;
   p->total_bytes = p->feats_bytes + p->mask_bytes + p->flag_bytes;
@@ -228,35 +252,39 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   }
 #endif
 
-  // Tile-pipelined sweep (sweep_tiled.cuh): whenever the geometry is shared by the frames and the features are staged
-  // as fp32.  Tile = 8 rows x 16 pixels; one chunk of the geometry table per (tile, candidate).
-  p->tiled = !p->per_frame_grids && !(a->flags & (MVSGI_FLAG_FEATS_BF16 | MVSGI_FLAG_CTA_TABLE)) && !p->walk &&
-             env_int("MVSGI_TILED", 1) != 0;
   p->table_bytes = 0;
+#ifdef MVSGI_EXPERIMENTS
   if (p->tiled) {
+    const int tw = mvsgi::tiled_warps_per_cta(), tv = tw * 8;  // octets / voxels per tile
+    // tile = tile_h rows x (kTileWarps / tile_h) octets; one chunk of the geometry table per (tile, candidate)
     p->tile_h = env_int("MVSGI_TILE_H", 8);
-    if (p->tile_h != 16 && p->tile_h != 8 && p->tile_h != 4 && p->tile_h != 2 && p->tile_h != 1) p->tile_h = 8;
-    p->oct_per_row = mvsgi::kTileWarps / p->tile_h;
+    if (p->tile_h < 1 || tw % p->tile_h != 0) p->tile_h = tw >= 8 ? 8 : tw;
+    p->oct_per_row = tw / p->tile_h;
     p->tiles_x = (a->out_w + p->oct_per_row * 8 - 1) / (p->oct_per_row * 8);
     p->num_tiles = p->tiles_x * ((a->out_h + p->tile_h - 1) / p->tile_h);
-    const int rec_bytes = a->num_cams * mvsgi::kTileVox * 16;
+    const int rec_bytes = a->num_cams * tv * 16;
     p->minfo_off = rec_bytes;
-    p->vinfo_off = rec_bytes + (p->per_frame_masks ? mvsgi::kTileVox * 16 : 0);
-    p->chunk_bytes = p->vinfo_off + mvsgi::kTileVox * 4;
+    p->vinfo_off = rec_bytes + (p->per_frame_masks ? tv * 16 : 0);
+    p->chunk_bytes = p->vinfo_off + tv * 4;
+    // frames per pass: records and weights are decoded once for 2 frames whenever there are 2
+    p->frames_per_pass = a->batch >= 2 ? env_int("MVSGI_FRAMES_PER_PASS", 2) : 1;
+    if (p->frames_per_pass != 2) p->frames_per_pass = 1;
+    p->frame_groups = (a->batch + p->frames_per_pass - 1) / p->frames_per_pass;
+    const int tiled_target = device_sms() * mvsgi::tiled_ctas_per_sm();
     // enough items to keep every CTA busy and the tail short: split the candidates of a tile when frames x tiles is small
-    const int64_t want = 8ll * grid_target;
+    const int64_t want = 8ll * tiled_target;
     int ipt = 1;
-    while ((int64_t)a->batch * p->num_tiles * ipt < want && ipt * 2 <= a->num_cands) ipt *= 2;
+    while ((int64_t)p->frame_groups * p->num_tiles * ipt < want && ipt * 2 <= a->num_cands) ipt *= 2;
     p->steps_per_item = (a->num_cands + ipt - 1) / ipt;
     p->items_per_tile = (a->num_cands + p->steps_per_item - 1) / p->steps_per_item;
-    const int64_t items = (int64_t)a->batch * p->num_tiles * p->items_per_tile;
+    const int64_t items = (int64_t)p->frame_groups * p->num_tiles * p->items_per_tile;
     if (items >= (1ll << 30)) return MVSGI_E_SHAPE;
     p->tiled_items = (int)items;
-    p->tiled_grid = (int)(items < grid_target ? items : grid_target);
+    p->tiled_grid = (int)(items < tiled_target ? items : tiled_target);
     p->table_bytes = align_up((int64_t)p->num_tiles * a->num_cands * p->chunk_bytes, 256);
-    p->tiled_smem = (size_t)mvsgi::kTileStages * p->chunk_bytes + mvsgi::kTileStages * (8 + 8 + 16 + 16);
     p->total_bytes += p->table_bytes;
   }
+#endif
   return MVSGI_OK;
 }
 
@@ -270,12 +298,25 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   kp.P = a->out_h * a->out_w; kp.numRuns = p.num_runs; kp.runLen = p.run_len; kp.dch = p.dch;
   kp.numChunks = p.num_chunks; kp.numItems = p.num_items; kp.maxPairs = p.max_pairs; kp.grpPx = p.group_px; kp.interleave = p.interleave;
   kp.wL = p.walk ? p.w_len : 0; kp.wSegs = p.walk ? p.w_segs : 0; kp.wNumSeg = p.walk ? p.w_num_seg : 0;
-  kp.feat = ws_feats;
-  kp.fsY = Wp * mvsgi::kCG;
-  kp.fsCg = Hp1 * kp.fsY;
-  kp.fsCam = kp.fsCg * p.cg;
-  kp.fsB = (long long)kp.fsCam * a->num_cams;
-  kp.zeroOff = (a->feat_h + 1) * kp.fsY;  // rows Hf+1 and Hf+2 are all zero
+  if (p.direct) {  // the caller's channels-last tensor: element (b, cam, y, x, c) at b*s0 + cam*s1 + y*s3 + x*s4 + c
+    kp.feat = a->feats;
+    kp.fsY = (int)a->feats_stride[3];
+    kp.fsCg = mvsgi::kCG;
+    kp.fsCam = (int)a->feats_stride[1];
+    kp.fsB = a->feats_stride[0];
+    kp.zeroOff = 0;
+    kp.direct = 1;
+    kp.fX = (int)a->feats_stride[4];
+  } else {
+    kp.feat = ws_feats;
+    kp.fsY = Wp * mvsgi::kCG;
+    kp.fsCg = Hp1 * kp.fsY;
+    kp.fsCam = kp.fsCg * p.cg;
+    kp.fsB = (long long)kp.fsCam * a->num_cams;
+    kp.zeroOff = (a->feat_h + 1) * kp.fsY;  // rows Hf+1 and Hf+2 are all zero
+    kp.direct = 0;
+    kp.fX = mvsgi::kCG;
+  }
   if (p.pack_masks) {
     kp.mbits = ws_bits;
     kp.mPitch = p.mask_pitch;
@@ -343,12 +384,17 @@ void launch_softargmin_x2(const mvsgi::SoftKP& kp, dim3 grid, cudaStream_t st) {
   else launch_x2_flags<16, false>(kp, grid, st);
 }
 
-void fill_tp(const SweepPlan& p, unsigned char* table, int* queue, mvsgi::TiledKP& tp) {
+#ifdef MVSGI_EXPERIMENTS
+void fill_tp(const MvsgiSweepArgs* a, const SweepPlan& p, unsigned char* table, int* queue, mvsgi::TiledKP& tp) {
   tp.tileH = p.tile_h; tp.octPerRow = p.oct_per_row; tp.tilesX = p.tiles_x; tp.numTiles = p.num_tiles;
-  tp.stepsPerItem = p.steps_per_item; tp.itemsPerTile = p.items_per_tile; tp.numItems = p.tiled_items;
+  tp.stepsPerItem = p.steps_per_item; tp.itemsPerTile = p.items_per_tile; tp.frameGroups = p.frame_groups;
+  tp.numItems = p.tiled_items;
   tp.chunkBytes = p.chunk_bytes; tp.minfoOff = p.minfo_off; tp.vinfoOff = p.vinfo_off;
+  tp.fX = p.direct ? (int)a->feats_stride[4] : mvsgi::kCG;
+  tp.direct = p.direct ? 1 : 0;
   tp.table = table; tp.queue = queue;
 }
+#endif
 
 }  // namespace
 
@@ -364,7 +410,9 @@ int backward_plan(const MvsgiSweepBwdArgs* a, MvsgiSweepArgs* f, SweepPlan* p) {
   f->vol = const_cast<float*>(a->grad_vol);  // only has to be non-NULL for validation; never written
   f->valid_out = nullptr;
   f->num_peers = 0;
-  f->flags = MVSGI_FLAG_CTA_TABLE;  // the backward only uses the staging part of the plan: no geometry table in its workspace
+  // the backward only uses the staging part of the plan: no geometry table in its workspace, features always staged
+  // (the gradient image it scatters into has the staged layout)
+  f->flags = MVSGI_FLAG_CTA_TABLE | MVSGI_FLAG_STAGED_FEATS;
   return validate_and_plan(f, p);
 }
 
@@ -428,7 +476,7 @@ int mvsgi_sweep_launch_count(const MvsgiSweepArgs* a) {
   SweepPlan p;
   const int rc = validate_and_plan(a, &p);
   if (rc != MVSGI_OK) return rc;
-  const int stage = 1 + (p.pack_masks ? 1 : 0);
+  const int stage = (p.direct ? 0 : 1) + (p.pack_masks ? 1 : 0);
   if (a->flags & MVSGI_FLAG_STAGE_ONLY) return stage;
   const int sweep = p.tiled ? 2 : 1;  // geometry table + sweep
   if (a->flags & MVSGI_FLAG_SWEEP_ONLY) return sweep;
@@ -462,8 +510,8 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
   const bool do_sweep = !(a->flags & MVSGI_FLAG_STAGE_ONLY);
   const int Wp = a->feat_w + 2, Hp1 = a->feat_h + 3;
 
-  // 1. features -> zero-padded channel-group-major channels-last
-  if (do_stage) {
+  // 1. features -> zero-padded channel-group-major channels-last (not when they are tapped where they are)
+  if (do_stage && !p.direct) {
     const int N = a->batch * a->num_cams;
     const int x_blocks = (Wp + mvsgi::kStagePx - 1) / mvsgi::kStagePx;
     if ((int64_t)N * p.cg * x_blocks >= (1ll << 31) || Hp1 > 65535) return MVSGI_E_SHAPE;
@@ -504,21 +552,21 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
   else memset(&rig, 0, sizeof(rig));
 
   cudaError_t e;
+#ifdef MVSGI_EXPERIMENTS
   if (p.tiled) {
     // geometry table (once per call, shared by all frames), then the item queue counter, then the sweep
     int* queue = ws_flags + 32;
     mvsgi::TiledKP tp;
-    fill_tp(p, (unsigned char*)(ws + p.feats_bytes + p.mask_bytes + p.flag_bytes), queue, tp);
+    fill_tp(a, p, (unsigned char*)(ws + p.feats_bytes + p.mask_bytes + p.flag_bytes), queue, tp);
     e = mvsgi::launch_tile_table(a->aggregate, a->num_cams, kp, tp, rig, st);
     if (e != cudaSuccess) return (int)e;
     g_launches++;
     e = cudaMemsetAsync(queue, 0, sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
-    e = mvsgi::launch_sweep_tiled(a->aggregate, a->num_cams, kp, tp, p.tiled_grid, p.tiled_smem, st);
+    e = mvsgi::launch_sweep_tiled(a->aggregate, a->num_cams, kp, tp, p.tiled_grid, p.frames_per_pass, st);
     g_launches++;
     return (int)e;
   }
-#ifdef MVSGI_EXPERIMENTS
   if (p.walk) {
     e = mvsgi::launch_sweep_walk(a->aggregate, a->num_cams, kp, rig, p.grid, p.smem_bytes, st);
     g_launches++;
@@ -616,7 +664,7 @@ int mvsgi_sweep_backward_f32(const MvsgiSweepBwdArgs* a, void* stream) {
   // 1. stage feats + pack masks exactly as the forward does
   f.workspace = ws;
   f.workspace_bytes = p.total_bytes;
-  f.flags = MVSGI_FLAG_STAGE_ONLY;
+  f.flags |= MVSGI_FLAG_STAGE_ONLY;  // on top of the plan's flags (staged features, no geometry table)
   rc = mvsgi_sweep_f32(&f, stream);
   if (rc != MVSGI_OK) return rc;
   // 2. zero the staged gradient image

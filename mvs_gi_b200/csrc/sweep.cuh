@@ -52,6 +52,9 @@ struct SweepKP {
   const float* feat;
   long long fsB;
   int fsCam, fsCg, fsY, zeroOff;  // host checks CAM * fsCam < 2^31
+  // direct = 1: `feat` is the caller's channels-last tensor (no zero frame, nothing staged): element (b, cam, y, x, c)
+  // at feat[b*fsB + cam*fsCam + y*fsY + x*fX + c], fsCg = 16; tap-table offsets then carry edge flags (make_entry_direct)
+  int direct, fX;
   // packed masks (std): uint32 words, image (b, cam) at mbits + b*mbB + cam*mbCam, (Hm+2) rows of mPitch words
   const uint32_t* mbits;
   long long mbB, mbCam;
@@ -70,6 +73,35 @@ struct SweepKP {
   long long peerDelta[MVSGI_MAX_PEERS];
 };
 
+// ---- packed fp32 (FMUL2 / FFMA2 / FADD2 of sm_100: half the issue slots of the scalar form, same bits)
+// packed fp32 (two lanes of one 64-bit register, IEEE round-to-nearest per lane) ---------------------------------
+typedef unsigned long long f32x2;
+MVSGI_DEV f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+MVSGI_DEV void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+MVSGI_DEV f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+MVSGI_DEV f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+MVSGI_DEV f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+MVSGI_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 MVSGI_DEV float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 // bf16-staged features (MVSGI_FLAG_FEATS_BF16): 4 channels = 8 bytes, widened to fp32 exactly (bf16 is the top half)
 MVSGI_DEV float4 ldg4(const uint16_t* p) {
@@ -168,6 +200,32 @@ MVSGI_DEV void make_entry(const SweepKP& kp, float gx, float gy, int& off, float
   }
 }
 
+// The same entry for features that are tapped where they are (channels-last, no zero frame; backports.py:58-72 pads and
+// clamps instead).  The offset is a multiple of 16 elements, so its low 4 bits carry what the padding would have done:
+//   bits 0-1  xmode  0: columns x0, x0 + 1   1: column x0 is padding — both taps read column x0 + 1, its weight hx := 0
+//                                            2: column x0 + 1 is padding — both read column x0, lx := 0
+//   bits 2-3  ymode  likewise for rows y0, y0 + 1 (hy := 0 / ly := 0)
+// A padding tap thus reads a real pixel with weight exactly 0, which adds the same +0 the zero frame would (for finite
+// features).  Samples entirely outside read pixel 0 with all weights 0.
+MVSGI_DEV void make_entry_direct(const SweepKP& kp, float gx, float gy, int& off, float& lx, float& ly) {
+  const float x = unnormalise(gx, kp.Wf), y = unnormalise(gy, kp.Hf);
+  if (!(x >= -1.0f && x < (float)kp.Wf && y >= -1.0f && y < (float)kp.Hf)) {
+    off = 1 | (1 << 2);  // xmode 1, ymode 1 with lx = ly = 0: all four weights are 0
+    lx = 0.0f;
+    ly = 0.0f;
+    return;
+  }
+  const float fx0 = floorf(x), fy0 = floorf(y);
+  int x0 = (int)fx0, y0 = (int)fy0, xmode = 0, ymode = 0;
+  if (x0 < 0) { x0 = 0; xmode = 1; }
+  else if (x0 >= kp.Wf - 1) xmode = 2;
+  if (y0 < 0) { y0 = 0; ymode = 1; }
+  else if (y0 >= kp.Hf - 1) ymode = 2;
+  off = (y0 * kp.fsY + x0 * kp.fX) | (ymode << 2) | xmode;
+  lx = fsub(x, fx0);
+  ly = fsub(y, fy0);
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------------------------
 // Shared-memory tap table: one record of kEntryWords(CAM) words per (candidate, pixel) pair
 //   [0] output offset d*Ho*Wo + h*Wo + w   [1] validity bits of the cameras (rewritten per frame if masks are per frame)
@@ -175,7 +233,7 @@ MVSGI_DEV void make_entry(const SweepKP& kp, float gx, float gy, int& off, float
 // The record stride is odd, so the 8 records a warp reads at a time sit in 8 different banks.
 __host__ __device__ constexpr int entry_words(int cam) { return (2 + 3 * cam) | 1; }
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16>
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16, bool DIRECT = false>
 __global__ void __launch_bounds__(kSweepThreads, kSweepCtas)
 sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -254,7 +312,8 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         }
         int off;
         float lx, ly;
-        make_entry(kp, gx, gy, off, lx, ly);
+        if (DIRECT) make_entry_direct(kp, gx, gy, off, lx, ly);
+        else make_entry(kp, gx, gy, off, lx, ly);
         uint32_t* rec = tab + (size_t)j * ES;
         rec[2 + 3 * cam] = (uint32_t)(off + cam * kp.fsCam);
         rec[3 + 3 * cam] = __float_as_uint(lx);
@@ -312,8 +371,8 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       const FT* fbq = reinterpret_cast<const FT*>(kp.feat) + (long long)b * kp.fsB + cLane;
       // NCDHW: voxel (c, po) at frame + c*cs + po; channels-last: at frame + po*Cout + c
       float* vq = kp.vol + (long long)b * kp.Cout * cs + (CL ? (long long)cLane : (long long)cLane * cs);
-      int fsY = kp.fsY, zeroOff = kp.zeroOff, csr = cs;
-      asm volatile("" : "+l"(fbq), "+l"(vq), "+r"(fsY), "+r"(zeroOff), "+r"(csr));
+      int fsY = kp.fsY, zeroOff = kp.zeroOff, csr = cs, fX = kp.fX;
+      asm volatile("" : "+l"(fbq), "+l"(vq), "+r"(fsY), "+r"(zeroOff), "+r"(csr), "+r"(fX));
 
       const int q8 = lane >> 2;
       const int vsh = (b & 1) * 8;
@@ -329,29 +388,47 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         float* vcg = vq + (CL ? (long long)po * kp.Cout : (long long)po);
 
         for (int cg = 0; cg < kp.CG; ++cg, fcg += kp.fsCg, vcg += (CL ? (long long)kCG : kCG * (long long)csr)) {
-          float f[CAM][4];
+          f32x2 f[CAM][2];  // this lane's 4 channels of every camera's sample, as two packed pairs
 #pragma unroll
           for (int cam = 0; cam < CAM; ++cam) {
             const bool ld = need && ((v >> cam) & 1u);
             if (__any_sync(0xFFFFFFFFu, ld)) {
               // lanes with nothing to sample read the all-zero patch with zero weights: no divergence, no predication
-              const int off = ld ? (int)rec[2 + 3 * cam] : zeroOff;
-              const float lx = __uint_as_float(rec[3 + 3 * cam]), ly = __uint_as_float(rec[4 + 3 * cam]);
-              const float hx = ld ? 1.0f - lx : 0.0f, hy = 1.0f - ly;
-              const float lxe = ld ? lx : 0.0f;
+              // (DIRECT: their own, always valid, taps with zero weights)
+              const int offr = (int)rec[2 + 3 * cam];
+              const int off = DIRECT ? (offr & ~15) : (ld ? offr : zeroOff);
+              const float lx = __uint_as_float(rec[3 + 3 * cam]);
+              float ly = __uint_as_float(rec[4 + 3 * cam]);
+              float hx = ld ? 1.0f - lx : 0.0f, hy = 1.0f - ly;
+              float lxe = ld ? lx : 0.0f;
               const FT* t = fcg + off;
               const FT* t1 = t + fsY;
-              const float4 ta = ldg4(t), tc = ldg4(t + kCG), tb = ldg4(t1), td = ldg4(t1 + kCG);
+              float4 ta, tb, tc, td;
+              if (DIRECT && ((offr & 15) != 0 || fX != kCG)) {
+                // image edges: the padding tap re-reads its real neighbour with weight 0 (make_entry_direct); also the
+                // general pixel pitch (C > 16)
+                const int xm = offr & 3, ym = (offr >> 2) & 3;
+                if (xm == 1) hx = 0.0f;
+                if (xm == 2) lxe = 0.0f;
+                if (ym == 1) hy = 0.0f;
+                if (ym == 2) ly = 0.0f;
+                if (ym) t1 = t;
+                const int dx = xm ? 0 : fX;
+                ta = ldg4(t), tc = ldg4(t + dx), tb = ldg4(t1), td = ldg4(t1 + dx);
+              } else {
+                ta = ldg4(t), tc = ldg4(t + kCG), tb = ldg4(t1), td = ldg4(t1 + kCG);
+              }
               const float wa = __fmul_rn(hx, hy), wb = __fmul_rn(hx, ly), wc = __fmul_rn(lxe, hy),
                           wd = __fmul_rn(lxe, ly);  // backports.py:52-55
-              // backports.py:86  Ia*wa + Ib*wb + Ic*wc + Id*wd, summed as (column x0) + (column x1) — the same
-              // bits as sweep_walk.cuh, which keeps the two columns of a patch in registers
-              f[cam][0] = __fadd_rn(fmaf(tb.x, wb, __fmul_rn(ta.x, wa)), fmaf(td.x, wd, __fmul_rn(tc.x, wc)));
-              f[cam][1] = __fadd_rn(fmaf(tb.y, wb, __fmul_rn(ta.y, wa)), fmaf(td.y, wd, __fmul_rn(tc.y, wc)));
-              f[cam][2] = __fadd_rn(fmaf(tb.z, wb, __fmul_rn(ta.z, wa)), fmaf(td.z, wd, __fmul_rn(tc.z, wc)));
-              f[cam][3] = __fadd_rn(fmaf(tb.w, wb, __fmul_rn(ta.w, wa)), fmaf(td.w, wd, __fmul_rn(tc.w, wc)));
+              // backports.py:86  Ia*wa + Ib*wb + Ic*wc + Id*wd, summed as (column x0) + (column x1), two channels per
+              // instruction
+              const f32x2 WA = pk2(wa, wa), WB = pk2(wb, wb), WC = pk2(wc, wc), WD = pk2(wd, wd);
+              f[cam][0] = add2(fma2(pk2(tb.x, tb.y), WB, mul2(pk2(ta.x, ta.y), WA)),
+                               fma2(pk2(td.x, td.y), WD, mul2(pk2(tc.x, tc.y), WC)));
+              f[cam][1] = add2(fma2(pk2(tb.z, tb.w), WB, mul2(pk2(ta.z, ta.w), WA)),
+                               fma2(pk2(td.z, td.w), WD, mul2(pk2(tc.z, tc.w), WC)));
             } else {
-              f[cam][0] = f[cam][1] = f[cam][2] = f[cam][3] = 0.0f;
+              f[cam][0] = f[cam][1] = 0ull;
             }
           }
 
@@ -360,20 +437,23 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
             float o[4] = {0.f, 0.f, 0.f, 0.f};
             if (need) {
               const float inv = n == 2 ? 0.5f : (n == 3 ? (1.0f / 3.0f) : 0.25f);
+              const f32x2 INV = pk2(inv, inv);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float s = f[0][i];
+              for (int i = 0; i < 2; ++i) {
+                f32x2 s = f[0][i];
 #pragma unroll
-                for (int cam = 1; cam < CAM; ++cam) s += f[cam][i];
-                const float avg = s * inv;  // :114
-                float acc = 0.f;
+                for (int cam = 1; cam < CAM; ++cam) s = add2(s, f[cam][i]);
+                // :114  every step rounds on its own, as the reference's separate tensor ops do.  The mean is an fma
+                // with +0: ptxas contracts mul.rn.f32x2 + sub.rn.f32x2 into one FFMA2, which would round once.
+                const f32x2 avg = fma2(s, INV, 0ull);
+                f32x2 acc = 0ull;
 #pragma unroll
                 for (int cam = 0; cam < CAM; ++cam) {
                   // :119-122 masked-out cameras contribute (avg-avg)^2 = 0
-                  const float dlt = ((v >> cam) & 1u) ? f[cam][i] - avg : 0.0f;
-                  acc = fmaf(dlt, dlt, acc);
+                  const f32x2 dlt = ((v >> cam) & 1u) ? sub2(f[cam][i], avg) : 0ull;
+                  acc = fma2(dlt, dlt, acc);
                 }
-                o[i] = acc * inv;
+                unpk2(mul2(acc, INV), o[2 * i], o[2 * i + 1]);
               }
             }
             if (act) {
@@ -388,9 +468,12 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
 #pragma unroll
               for (int cam = 0; cam < CAM; ++cam) {
                 float* dst = vcg + (CL ? (long long)(cam * kp.C) : (long long)(cam * kp.C) * csr);
-                st_lane<CL>(dst, f[cam], nst, csr);
+                float fc[4];
+                unpk2(f[cam][0], fc[0], fc[1]);
+                unpk2(f[cam][1], fc[2], fc[3]);
+                st_lane<CL>(dst, fc, nst, csr);
                 if (PEERS) {
-                  for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(dst + kp.peerDelta[pr], f[cam], nst, csr);
+                  for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(dst + kp.peerDelta[pr], fc, nst, csr);
                 }
               }
             }

@@ -7,9 +7,9 @@
 namespace mvsgi {
 namespace {
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16 = false>
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16 = false, bool DIRECT = false>
 cudaError_t launch_sweep_cl(const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
-  auto kern = sweep_kernel<CAM, AGG, FULLC, VALID, PEERS, CL, BF16>;
+  auto kern = sweep_kernel<CAM, AGG, FULLC, VALID, PEERS, CL, BF16, DIRECT>;
   static DynSmemSet smem_set;  // per instantiation
   cudaError_t e = ensure_dyn_smem(kern, smem, smem_set);
   if (e != cudaSuccess) return e;
@@ -19,6 +19,9 @@ cudaError_t launch_sweep_cl(const SweepKP& kp, const MvsgiRig& rig, int grid, si
 
 template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS = false>
 cudaError_t launch_sweep(const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
+  if (FULLC && kp.direct)  // channels-last features tapped in place (always whole 16-channel groups)
+    return kp.volChannelsLast ? launch_sweep_cl<CAM, AGG, FULLC, VALID, PEERS, true, false, FULLC>(kp, rig, grid, smem, st)
+                              : launch_sweep_cl<CAM, AGG, FULLC, VALID, PEERS, false, false, FULLC>(kp, rig, grid, smem, st);
   return kp.volChannelsLast ? launch_sweep_cl<CAM, AGG, FULLC, VALID, PEERS, true>(kp, rig, grid, smem, st)
                             : launch_sweep_cl<CAM, AGG, FULLC, VALID, PEERS, false>(kp, rig, grid, smem, st);
 }

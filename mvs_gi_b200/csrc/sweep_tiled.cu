@@ -1,4 +1,4 @@
-// sweep_tiled.cu — launchers of the tile-pipelined sweep (sweep_tiled.cuh).
+// sweep_tiled.cu — launchers of the tile-walking sweep (sweep_tiled.cuh).
 #include "launch.h"
 
 namespace mvsgi {
@@ -21,46 +21,49 @@ cudaError_t table_agg(int cams, const SweepKP& kp, const TiledKP& tp, const Mvsg
   }
 }
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL>
-cudaError_t launch_k(const SweepKP& kp, const TiledKP& tp, int grid, size_t smem, cudaStream_t st) {
-  auto kern = sweep_tiled_kernel<CAM, AGG, FULLC, VALID, PEERS, CL>;
-  static DynSmemSet smem_set;  // per instantiation
-  cudaError_t e = ensure_dyn_smem(kern, smem, smem_set);
+template <int CAM, int AGG, bool CL, int FB>
+cudaError_t launch_k(const SweepKP& kp, const TiledKP& tp, int grid, cudaStream_t st) {
+  auto kern = sweep_tiled_kernel<CAM, AGG, CL, FB>;
+  // no shared memory to speak of: give the whole SM to L1 (the taps live there)
+  static bool carveout_set[kMaxDevices] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kTileThreads, smem, st>>>(kp, tp);
+  if (dev >= 0 && dev < kMaxDevices && !carveout_set[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    if (e != cudaSuccess) return e;
+    carveout_set[dev] = true;
+  }
+  kern<<<grid, kTileThreads, 0, st>>>(kp, tp);
   return cudaGetLastError();
 }
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS>
-cudaError_t launch_cl(const SweepKP& kp, const TiledKP& tp, int grid, size_t smem, cudaStream_t st) {
-  return kp.volChannelsLast ? launch_k<CAM, AGG, FULLC, VALID, PEERS, true>(kp, tp, grid, smem, st)
-                            : launch_k<CAM, AGG, FULLC, VALID, PEERS, false>(kp, tp, grid, smem, st);
-}
-
 template <int CAM, int AGG>
-cudaError_t launch_flags(const SweepKP& kp, const TiledKP& tp, int grid, size_t smem, cudaStream_t st) {
-  const bool fullc = kp.C % kCG == 0;
-  if (kp.numPeers > 0)
-    return fullc ? launch_cl<CAM, AGG, true, false, true>(kp, tp, grid, smem, st)
-                 : launch_cl<CAM, AGG, false, false, true>(kp, tp, grid, smem, st);
-  if (AGG == MVSGI_AGG_STD && kp.validOut != nullptr)
-    return fullc ? launch_cl<CAM, AGG, true, true, false>(kp, tp, grid, smem, st)
-                 : launch_cl<CAM, AGG, false, true, false>(kp, tp, grid, smem, st);
-  return fullc ? launch_cl<CAM, AGG, true, false, false>(kp, tp, grid, smem, st)
-               : launch_cl<CAM, AGG, false, false, false>(kp, tp, grid, smem, st);
+cudaError_t launch_flags(const SweepKP& kp, const TiledKP& tp, int grid, int fb, cudaStream_t st) {
+#ifdef MVSGI_TILE_ONLY_BENCH  // experiment builds: only the bench shape (3 cameras, std, channels-last volume)
+  if (CAM != 3 || AGG != MVSGI_AGG_STD || !kp.volChannelsLast) return cudaErrorNotSupported;
+  return fb == 2 ? launch_k<3, MVSGI_AGG_STD, true, 2>(kp, tp, grid, st) : launch_k<3, MVSGI_AGG_STD, true, 1>(kp, tp, grid, st);
+#else
+  if (kp.volChannelsLast)
+    return fb == 2 ? launch_k<CAM, AGG, true, 2>(kp, tp, grid, st) : launch_k<CAM, AGG, true, 1>(kp, tp, grid, st);
+  return fb == 2 ? launch_k<CAM, AGG, false, 2>(kp, tp, grid, st) : launch_k<CAM, AGG, false, 1>(kp, tp, grid, st);
+#endif
 }
 
 template <int AGG>
-cudaError_t launch_agg(int cams, const SweepKP& kp, const TiledKP& tp, int grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_agg(int cams, const SweepKP& kp, const TiledKP& tp, int grid, int fb, cudaStream_t st) {
   switch (cams) {
-    case 1: return launch_flags<1, AGG>(kp, tp, grid, smem, st);
-    case 2: return launch_flags<2, AGG>(kp, tp, grid, smem, st);
-    case 3: return launch_flags<3, AGG>(kp, tp, grid, smem, st);
-    default: return launch_flags<4, AGG>(kp, tp, grid, smem, st);
+    case 1: return launch_flags<1, AGG>(kp, tp, grid, fb, st);
+    case 2: return launch_flags<2, AGG>(kp, tp, grid, fb, st);
+    case 3: return launch_flags<3, AGG>(kp, tp, grid, fb, st);
+    default: return launch_flags<4, AGG>(kp, tp, grid, fb, st);
   }
 }
 
 }  // namespace
+
+int tiled_warps_per_cta() { return kTileWarps; }
+int tiled_ctas_per_sm() { return kTileCtas; }
 
 cudaError_t launch_tile_table(int aggregate, int cams, const SweepKP& kp, const TiledKP& tp, const MvsgiRig& rig,
                               cudaStream_t st) {
@@ -68,10 +71,10 @@ cudaError_t launch_tile_table(int aggregate, int cams, const SweepKP& kp, const 
                                     : table_agg<MVSGI_AGG_CONCAT>(cams, kp, tp, rig, st);
 }
 
-cudaError_t launch_sweep_tiled(int aggregate, int cams, const SweepKP& kp, const TiledKP& tp, int grid, size_t smem,
+cudaError_t launch_sweep_tiled(int aggregate, int cams, const SweepKP& kp, const TiledKP& tp, int grid, int frames_per_pass,
                                cudaStream_t st) {
-  return aggregate == MVSGI_AGG_STD ? launch_agg<MVSGI_AGG_STD>(cams, kp, tp, grid, smem, st)
-                                    : launch_agg<MVSGI_AGG_CONCAT>(cams, kp, tp, grid, smem, st);
+  return aggregate == MVSGI_AGG_STD ? launch_agg<MVSGI_AGG_STD>(cams, kp, tp, grid, frames_per_pass, st)
+                                    : launch_agg<MVSGI_AGG_CONCAT>(cams, kp, tp, grid, frames_per_pass, st);
 }
 
 }  // namespace mvsgi

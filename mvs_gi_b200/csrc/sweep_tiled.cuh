@@ -1,84 +1,134 @@
-// sweep_tiled.cuh — the tile-pipelined sweep (round 2): same arithmetic as sweep.cuh, different work decomposition.
+// sweep_tiled.cuh — the tile-walking sweep (round 2): same arithmetic as sweep.cuh, different work decomposition.
 //
 // Replaces (dsta_mvs/model/...): cost_volume_builder/spherical_sweep_avg.py:38-136, spherical_sweep.py:38-68,
 // backports/backports.py:11-86 — bit-identical to sweep_kernel (sweep.cuh) on the same inputs.
 //
 // Why a second decomposition.  sweep_kernel keeps the tap table of a CTA's pixels (80 KB) in shared memory for the
-// whole launch; two CTAs leave 68 KB of L1 for the taps and each CTA's pixels are scattered octets, so only 26 % of
-// the tap sectors hit L1 (profiles/r1m_sweep_ncu.txt).  Here
+// whole launch; two CTAs leave 68 KB of L1 for the taps, each CTA's pixels are scattered octets, and only 26 % of the
+// tap sectors hit L1: 3.3 GB of L2->L1 traffic per 32-frame launch, three quarters of what the L2 can deliver
+// (profiles/r1m_sweep_ncu.txt), at 350 M issued instructions.  Here
 //   * the geometry of the whole volume is evaluated ONCE per launch by tile_table_kernel into a global table laid
-//     out as one contiguous chunk per (tile, candidate): per voxel and camera a 16-byte record, plus the mask lookup
-//     words / the static validity bits.  The table (20-26 MB at G16V) stays in the 126 MB L2 for all frames.
-//   * a persistent CTA takes work items (frame, tile, candidate range) from an atomic queue in frame-major order (all
-//     CTAs stay within a frame or two of each other, so a frame's features are read from HBM once), and a producer
-//     warp streams the item's chunks through a ring of shared-memory stages with TMA bulk copies
-//     (cp.async.bulk.shared::cluster.global + mbarrier complete_tx; SASS UBLKCP / SYNCS), 3 stages x <= 11 KB.
-//     ~170 KB of the SM's 228 KB stay L1.
-//   * a tile is a compact 8 x 16 block of output pixels and the 16 consumer warps walk its candidates in order: the
+//     out as one contiguous chunk per (tile, candidate): per voxel and camera a 16-byte record (tap offset + edge
+//     flags, the two column weights, frac y), plus the mask lookup words / the static validity bits.  The table
+//     (20-26 MB at G16V) stays in the 126 MB L2 for all frames; a warp reads its records with three 16-byte loads
+//     per candidate, one step ahead of their use, straight into registers (L1::no_allocate).  No shared memory:
+//     the whole 228 KB of the SM is L1 for the taps.
+//   * a tile is a compact block of output pixels (kTileWarps octets) and a CTA's warps walk its candidates in order: the
 //     sampling footprint of the tile slides along the epipolar direction by a few pixels per candidate, so what a
-//     candidate step needs is mostly what the previous one left in L1.
+//     candidate step needs is mostly what the previous one left in L1.  CTAs take (frame group, tile, candidate
+//     range) items from an atomic queue in frame-major order, so a frame's features are read from HBM once.
+//   * FB frames per pass (template): records, addresses and bilinear weights are decoded once and applied to FB
+//     frames, whose taps are all in flight together.
+//   * packed fp32 arithmetic (FMUL2 / FFMA2 / FADD2, two channels per instruction, round-to-nearest each): half the
+//     issue slots of the scalar form for the same bits.
 //   * the two quads of a quarter-warp (the 8 lanes one LDG.128 wavefront serves) always read 64-byte chunks in
 //     opposite halves of the 128-byte bank line: of its two patch columns (x0, x0 + 1) every quad loads first the
-//     one whose address bit 6 equals the quad's parity.  Measured (scripts/microbench/tap_banks.cu): 3.9 clk per
-//     request instead of 5.3 (L1-resident) — the data-pipe cost of a tap request is set by bank conflicts between the
-//     two chunks of a quarter-warp, not by the number of lines.  Column order does not change the result bits (the two
-//     column sums are added with one commutative fadd).
+//     one whose address bit 6 equals the quad's parity (scripts/microbench/tap_banks.cu: 3.9 clk per request instead
+//     of 5.3, L1-resident).  Column order does not change the result bits (one commutative add joins the columns).
+//   * features that are already channels-last (16 k channels, north_star (a)) are tapped in the caller's tensor: the
+//     record carries clamped offsets and edge flags instead of relying on a zero frame, so nothing is staged.
 #pragma once
 #include "sweep.cuh"
 
 namespace mvsgi {
 
-constexpr int kTileWarps = 16;                      // consumer warps per CTA = octets per tile
-constexpr int kTileVox = kTileWarps * 8;             // voxels per (tile, candidate) chunk
-constexpr int kTileThreads = (kTileWarps + 1) * 32;  // + the producer warp
-constexpr int kTileStages = 3;
+#ifndef MVSGI_TILE_WARPS
+#define MVSGI_TILE_WARPS 8
+#endif
+#ifndef MVSGI_TILE_CTAS
+#define MVSGI_TILE_CTAS 3
+#endif
+constexpr int kTileWarps = MVSGI_TILE_WARPS;  // warps per CTA = octets per tile
+constexpr int kTileVox = kTileWarps * 8;       // voxels per (tile, candidate) chunk
+constexpr int kTileThreads = kTileWarps * 32;
+constexpr int kTileCtas = MVSGI_TILE_CTAS;
 
 struct TiledKP {
   int tileH, octPerRow;  // tile = tileH rows x (octPerRow * 8) pixels, tileH * octPerRow == kTileWarps
   int tilesX, numTiles;
-  int stepsPerItem, itemsPerTile, numItems;  // item = (frame, tile, candidate range of <= stepsPerItem)
-  int chunkBytes, minfoOff, vinfoOff;        // chunk = rec[CAM][128] uint4 | minfo[128][4] u32 (per-frame masks) | vinfo[128] u32
-  unsigned char* table;                      // [numTiles][D] chunks
-  int* queue;                                // item counter, zero before the launch
+  int stepsPerItem, itemsPerTile, frameGroups, numItems;  // item = (frame group, tile, candidate range of <= stepsPerItem)
+  int chunkBytes, minfoOff, vinfoOff;  // chunk = rec[CAM][kTileVox] uint4 | minfo[kTileVox][4] u32 (per-frame masks) | vinfo[kTileVox] u32
+  int fX;                              // elements between horizontally adjacent feature pixels (16 staged, C direct)
+  int direct;                          // 1: kp.feat is the caller's channels-last tensor (no zero frame)
+  unsigned char* table;                // [numTiles][D] chunks
+  int* queue;                          // item counter, zero before the launch
 };
 
-// ---- mbarrier / TMA bulk copy (PTX) ----------------------------------------------------------------------------------
-MVSGI_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-MVSGI_DEV void mbar_init(uint64_t* b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+struct F4 {  // the 4 consecutive channels a lane owns, as two packed pairs
+  f32x2 lo, hi;
+};
+MVSGI_DEV F4 ldg_f4(const float* p) {
+  const ulonglong2 u = __ldg(reinterpret_cast<const ulonglong2*>(p));
+  F4 r;
+  r.lo = u.x;
+  r.hi = u.y;
+  return r;
 }
-MVSGI_DEV void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-MVSGI_DEV void mbar_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-MVSGI_DEV void mbar_wait(uint64_t* b, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      "WAIT_%=:\n"
-      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      " @p bra DONE_%=;\n"
-      " bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(b)),
-      "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy by the TMA unit; completes `bytes` of transaction on `bar`.  16-byte aligned, size % 16 == 0.
-MVSGI_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// table records: prefetched into L1 one candidate ahead (no registers held), then read from there
+MVSGI_DEV uint4 ld_rec(const unsigned char* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+MVSGI_DEV uint32_t ld_word(const unsigned char* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+MVSGI_DEV void prefetch_l1(const unsigned char* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+MVSGI_DEV void st_stream_f4(float* p, f32x2 lo, f32x2 hi) {
+  asm volatile("st.global.L1::no_allocate.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
 }
 
 // ---- geometry table ----------------------------------------------------------------------------------------------------
+// Record of (camera, voxel): { e | ymode << 2 | xcode, w_first, w_second, ly }            backports.py:41-72
+//   e        element offset (inside a frame's features, camera included, a multiple of 16) of row y0 of the patch
+//            column this quad loads FIRST — the one whose 64-byte chunk sits in the bank half of the quad's parity
+//   xcode    where the second column is: 0 at +fX elements, 2 at -fX, 1 the same column (image edge, its weight is 0)
+//   ymode    0: rows y0 and y0 + 1.  Image edges of un-padded features: 1: row y0 is the zero padding — both taps read
+//            row y0 + 1 and the y0 weight is forced to 0; 2: row y0 + 1 is the padding — both read row y0, ly := 0
+//   w_first, w_second   x weights of the two columns ((1 - lx, lx) in some order; 0 for a padding column)
+//   ly       y - y0
+// With staged (zero-framed) features xcode is 0 or 2 and ymode 0; samples whose four taps all fall into the padding
+// (and NaN coordinates) read the all-zero patch (staged) or pixel 0 with zero weights (direct).
+MVSGI_DEV uint4 make_record(const SweepKP& kp, const TiledKP& tp, int cam, int j, float gx, float gy) {
+  const float x = unnormalise(gx, kp.Wf), y = unnormalise(gy, kp.Hf);
+  uint4 r;
+  if (!(x >= -1.0f && x < (float)kp.Wf && y >= -1.0f && y < (float)kp.Hf)) {
+    r.x = (uint32_t)((tp.direct ? 0 : kp.zeroOff) + cam * kp.fsCam);
+    r.y = r.z = r.w = 0u;
+    return r;
+  }
+  const float fx0 = floorf(x), fy0 = floorf(y);
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const float lx = fsub(x, fx0), ly = fsub(y, fy0), hx = 1.0f - lx;
+  uint32_t ymode = 0, xcode;
+  int row, col;
+  float wf, ws;
+  if (!tp.direct) {
+    row = y0 + 1;
+    const int c0 = x0 + 1;  // padded coordinates
+    const uint32_t swap = ((uint32_t)((row * kp.fsY + c0 * tp.fX) >> 4) ^ (uint32_t)j) & 1u;
+    col = c0 + (int)swap;
+    xcode = swap ? 2u : 0u;
+    wf = swap ? lx : hx;
+    ws = swap ? hx : lx;
+  } else {
+    row = y0;
+    if (y0 < 0) { row = 0; ymode = 1u; }
+    else if (y0 >= kp.Hf - 1) { ymode = 2u; }
+    if (x0 < 0) {  // only column x0 + 1 = 0 is real
+      col = 0; xcode = 1u; wf = lx; ws = 0.0f;
+    } else if (x0 >= kp.Wf - 1) {  // only column x0 is real
+      col = x0; xcode = 1u; wf = hx; ws = 0.0f;
+    } else {
+      const uint32_t swap = ((uint32_t)((row * kp.fsY + x0 * tp.fX + cam * kp.fsCam) >> 4) ^ (uint32_t)j) & 1u;
+      col = x0 + (int)swap;
+      xcode = swap ? 2u : 0u;
+      wf = swap ? lx : hx;
+      ws = swap ? hx : lx;
+    }
+  }
+  r.x = (uint32_t)(row * kp.fsY + col * tp.fX + cam * kp.fsCam) | (ymode << 2) | xcode;
+  r.y = __float_as_uint(wf);
+  r.z = __float_as_uint(ws);
+  r.w = __float_as_uint(ly);
+  return r;
+}
+
 // grid (numTiles, D), block kTileVox: thread j = voxel j of the chunk (octet j / 8 of the tile, pixel j % 8 of it).
-// Record of (camera, voxel): { e0 | swap, cx0, cx1, ly }
-//   e0   element offset (inside a frame's staged features, camera included) of patch column x0, a multiple of 16
-//   swap (bit 0 of the same word) 1: this quad loads column x0 + 1 first, 0: column x0 first
-//   cx0, cx1  x weights of the first / second column ((1 - lx, lx) or swapped), ly = y - y0     backports.py:47-55
 template <int CAM, int AGG>
 __global__ void __launch_bounds__(kTileVox)
 tile_table_kernel(const SweepKP kp, const TiledKP tp, const __grid_constant__ MvsgiRig rig) {
@@ -110,18 +160,7 @@ tile_table_kernel(const SweepKP kp, const TiledKP tp, const __grid_constant__ Mv
       gy = g.y;
       if (AGG == MVSGI_AGG_STD) gvalid = __ldg(kp.gmask + cam * kp.gmCam + d * kp.gmD + hc * kp.gmY + wc * kp.gmX) != 0;
     }
-    int off;
-    float lx, ly;
-    make_entry(kp, gx, gy, off, lx, ly);
-    const uint32_t e = (uint32_t)(off + cam * kp.fsCam);
-    const uint32_t swap = ((e >> 4) ^ (uint32_t)j) & 1u;
-    const float hx = 1.0f - lx;
-    uint4 rr;
-    rr.x = e | swap;
-    rr.y = __float_as_uint(swap ? lx : hx);
-    rr.z = __float_as_uint(swap ? hx : lx);
-    rr.w = __float_as_uint(ly);
-    rec[cam * kTileVox + j] = rr;
+    rec[cam * kTileVox + j] = make_record(kp, tp, cam, j, gx, gy);
     if (AGG == MVSGI_AGG_STD) {
       const uint32_t mi = gvalid ? make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch) : kMaskNone;
       if (kp.perFrameMasks) minfo[j * 4 + cam] = mi;
@@ -138,261 +177,315 @@ tile_table_kernel(const SweepKP kp, const TiledKP tp, const __grid_constant__ Mv
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
-// One bilinear sample of 4 channels (backports.py:41-86).  r = the (camera, voxel) record; fb / fb2 = this lane's
-// pointers to rows y0 / y0 + 1 of the frame's staged features (element offset 0, channel quarter included).
-// The record holds the offset of column x0 with the swap bit in bit 0: this quad loads first the column whose bank
-// half matches its parity (x0 if swap == 0, else x0 + 1), then the other one.
-MVSGI_DEV void tile_sample(const float* __restrict__ fb, const float* __restrict__ fb2, const uint4 r, float cx0, float cx1,
-                           float f[4]) {
-  const int sw = (int)(r.x & 1u);
-  const int o0 = (int)r.x + 15 * sw;  // (x0 column | swap bit) -> first column:  + 16 * swap, bit 0 cleared
-  const int o1 = (int)r.x - 17 * sw;  // second column minus 16 elements (the + 16 is an immediate of the load)
-  const float ly = __uint_as_float(r.w), hy = 1.0f - ly;
-  const float4 a0 = ldg4(fb + o0), b0 = ldg4(fb2 + o0), a1 = ldg4(fb + o1 + 16), b1 = ldg4(fb2 + o1 + 16);
-  const float w00 = __fmul_rn(cx0, hy), w01 = __fmul_rn(cx0, ly), w10 = __fmul_rn(cx1, hy), w11 = __fmul_rn(cx1, ly);
-  // backports.py:86 as (column sum) + (column sum); which column comes first does not change the bits
-  f[0] = __fadd_rn(fmaf(b0.x, w01, __fmul_rn(a0.x, w00)), fmaf(b1.x, w11, __fmul_rn(a1.x, w10)));
-  f[1] = __fadd_rn(fmaf(b0.y, w01, __fmul_rn(a0.y, w00)), fmaf(b1.y, w11, __fmul_rn(a1.y, w10)));
-  f[2] = __fadd_rn(fmaf(b0.z, w01, __fmul_rn(a0.z, w00)), fmaf(b1.z, w11, __fmul_rn(a1.z, w10)));
-  f[3] = __fadd_rn(fmaf(b0.w, w01, __fmul_rn(a0.w, w00)), fmaf(b1.w, w11, __fmul_rn(a1.w, w10)));
+// A record decoded for this lane: element offsets of the four taps (first column rows y0 / y1, second column rows
+// y0 / y1) and the four weights.                                                          backports.py:52-55
+struct Taps {
+  int oa, ob, oc, od;
+  float w00, w01, w10, w11;
+};
+MVSGI_DEV Taps decode(const uint4 r, int fsY, int fX, float wf, float ws) {
+  Taps t;
+  const uint32_t xc = r.x & 3u, ym = (r.x >> 2) & 3u;
+  const int dx = (1 - (int)xc) * fX;
+  const int dy = ym ? 0 : fsY;
+  float ly = __uint_as_float(r.w);
+  float hy = 1.0f - ly;
+  if (ym == 1u) hy = 0.0f;
+  if (ym == 2u) ly = 0.0f;
+  t.oa = (int)(r.x & ~15u);
+  t.ob = t.oa + dy;
+  t.oc = t.oa + dx;
+  t.od = t.ob + dx;
+  t.w00 = __fmul_rn(wf, hy);
+  t.w01 = __fmul_rn(wf, ly);
+  t.w10 = __fmul_rn(ws, hy);
+  t.w11 = __fmul_rn(ws, ly);
+  return t;
+}
+// One bilinear sample of this lane's 4 channels: Ia*wa + Ib*wb + Ic*wc + Id*wd (backports.py:86), summed as
+// (first column) + (second column); which column comes first does not change the bits.
+MVSGI_DEV F4 sample4(const float* __restrict__ fb, const Taps& t) {
+  const F4 a0 = ldg_f4(fb + t.oa), b0 = ldg_f4(fb + t.ob), a1 = ldg_f4(fb + t.oc), b1 = ldg_f4(fb + t.od);
+  const f32x2 W00 = pk2(t.w00, t.w00), W01 = pk2(t.w01, t.w01), W10 = pk2(t.w10, t.w10), W11 = pk2(t.w11, t.w11);
+  F4 f;
+  f.lo = add2(fma2(b0.lo, W01, mul2(a0.lo, W00)), fma2(b1.lo, W11, mul2(a1.lo, W10)));
+  f.hi = add2(fma2(b0.hi, W01, mul2(a0.hi, W00)), fma2(b1.hi, W11, mul2(a1.hi, W10)));
+  return f;
 }
 
 // Variance across the cameras of the (compile-time) set V, spherical_sweep_avg.py:114-125: the same operations in the
-// same order as the generic loop below performs for that set (absent cameras add exact zeros there).
+// same order as sweep_kernel performs for that set (absent cameras add exact zeros there).
 template <int CAM, int V>
-MVSGI_DEV void tile_variance_uniform(const float f[CAM][4], float o[4]) {
+MVSGI_DEV F4 variance_uniform(const F4 (&f)[CAM]) {
   constexpr int n = ((V >> 0) & 1) + ((V >> 1) & 1) + ((V >> 2) & 1) + ((V >> 3) & 1);
   constexpr float inv = n == 2 ? 0.5f : (n == 3 ? (1.0f / 3.0f) : 0.25f);
+  const f32x2 INV = pk2(inv, inv);
+  F4 sm, acc, o;
+  bool first = true;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float sm = 0.f;
-    bool first = true;
+  for (int cam = 0; cam < CAM; ++cam)
+    if ((V >> cam) & 1) {
+      if (first) sm = f[cam];
+      else { sm.lo = add2(sm.lo, f[cam].lo); sm.hi = add2(sm.hi, f[cam].hi); }
+      first = false;
+    }
+  // :114  as an fma with +0 so that ptxas cannot contract the product into the subtraction below (it does contract
+  // mul.rn.f32x2 + sub.rn.f32x2 into FFMA2); sweep_kernel rounds the mean separately, like the reference's tensor ops
+  const f32x2 alo = fma2(sm.lo, INV, 0ull), ahi = fma2(sm.hi, INV, 0ull);
+  first = true;
 #pragma unroll
-    for (int cam = 0; cam < CAM; ++cam)
-      if ((V >> cam) & 1) {
-        sm = first ? f[cam][i] : sm + f[cam][i];
-        first = false;
-      }
-    const float avg = sm * inv;
-    float acc = 0.f;
-#pragma unroll
-    for (int cam = 0; cam < CAM; ++cam)
-      if ((V >> cam) & 1) {
-        const float dlt = f[cam][i] - avg;
-        acc = fmaf(dlt, dlt, acc);
-      }
-    o[i] = acc * inv;
+  for (int cam = 0; cam < CAM; ++cam)
+    if ((V >> cam) & 1) {
+      const f32x2 dlo = sub2(f[cam].lo, alo), dhi = sub2(f[cam].hi, ahi);  // :119-122
+      if (first) { acc.lo = mul2(dlo, dlo); acc.hi = mul2(dhi, dhi); }     // == fma(d, d, 0)
+      else { acc.lo = fma2(dlo, dlo, acc.lo); acc.hi = fma2(dhi, dhi, acc.hi); }
+      first = false;
+    }
+  o.lo = mul2(acc.lo, INV);
+  o.hi = mul2(acc.hi, INV);
+  return o;
+}
+
+// Everything a lane needs to store its 4 channels of one voxel of one frame.
+struct OutCtx {
+  float* vcg;          // this lane's first channel of the voxel (16-channel group 0)
+  long long validIdx;  // index into validOut
+  bool act;            // the voxel is inside the image
+};
+template <bool CL>
+MVSGI_DEV void store4(const SweepKP& kp, float* dst, const F4& o, int nst, int csr) {
+  if (CL) {
+    if (nst >= 4) st_stream_f4(dst, o.lo, o.hi);
+    if (kp.numPeers > 0 && nst >= 4) {
+#pragma unroll 1
+      for (int pr = 0; pr < kp.numPeers; ++pr) st_stream_f4(dst + kp.peerDelta[pr], o.lo, o.hi);
+    }
+  } else {
+    float v[4];
+    unpk2(o.lo, v[0], v[1]);
+    unpk2(o.hi, v[2], v[3]);
+    st_lane<false>(dst, v, nst, csr);
+    if (kp.numPeers > 0) {
+#pragma unroll 1
+      for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<false>(dst + kp.peerDelta[pr], v, nst, csr);
+    }
   }
 }
 
-// One octet of one candidate.  V >= 0: every voxel of the warp sees exactly the cameras of V (warp-uniform, compile
-// time): no votes, no selects, absent cameras are not touched.  V < 0: per-lane validity bits v.
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, int V>
-MVSGI_DEV void tile_octet(const SweepKP& kp, const uint4* __restrict__ rec, const float* fb, const float* fb2, float* vcg,
-                          uint32_t v, bool act, int q, int q8, int csr, long long validIdx) {
-  constexpr bool UNI = V >= 0;
-  const int n = UNI ? __popc((unsigned)V) : __popc(v);
-  const bool need = UNI ? true : (act && (AGG == MVSGI_AGG_CONCAT || n > 1));  // spherical_sweep_avg.py:106-111
-  for (int cg = 0; cg < kp.CG; ++cg, fb += kp.fsCg, fb2 += kp.fsCg, vcg += (CL ? (long long)kCG : kCG * (long long)csr)) {
-    float f[CAM][4];
+// One octet of one candidate for FB frames whose voxels all see exactly the cameras of V (warp-uniform, compile
+// time): no votes, no selects, absent cameras are not touched; the taps of all FB frames are independent loads.
+template <int CAM, int AGG, bool CL, int FB, int V>
+MVSGI_DEV void octet_uniform(const SweepKP& kp, const TiledKP& tp, const uint4 (&rec)[CAM], const float* const (&fb)[FB],
+                             const OutCtx (&oc)[FB], int q, int csr) {
+  constexpr int n = ((V >> 0) & 1) + ((V >> 1) & 1) + ((V >> 2) & 1) + ((V >> 3) & 1);
+  const float* fc[FB];
 #pragma unroll
-    for (int cam = 0; cam < CAM; ++cam) {
-      if (UNI) {
-        if ((V >> cam) & 1) {
-          const uint4 r = rec[cam * kTileVox];
-          tile_sample(fb, fb2, r, __uint_as_float(r.y), __uint_as_float(r.z), f[cam]);
-          // keep the next camera's 4 tap loads behind this camera's: 4 x 16 bytes in flight per lane is what the
-          // 56-register budget (2 CTAs x 17 warps) holds without spilling
-          asm volatile("" ::: "memory");
-        } else {
-          f[cam][0] = f[cam][1] = f[cam][2] = f[cam][3] = 0.0f;
-        }
-      } else {
-        const bool ld = need && ((v >> cam) & 1u);
-        if (__any_sync(0xFFFFFFFFu, ld)) {
-          uint4 r = rec[cam * kTileVox];
-          // lanes with nothing to sample read the all-zero patch (the pixel of it in this quad's bank half) with zero weights
-          if (!ld) r.x = (uint32_t)(kp.zeroOff + (q8 & 1) * 16);
-          tile_sample(fb, fb2, r, ld ? __uint_as_float(r.y) : 0.0f, ld ? __uint_as_float(r.z) : 0.0f, f[cam]);
-        } else {
-          f[cam][0] = f[cam][1] = f[cam][2] = f[cam][3] = 0.0f;
-        }
+  for (int k = 0; k < FB; ++k) fc[k] = fb[k];
+  for (int cg = 0; cg < kp.CG; ++cg) {
+    F4 f[FB][CAM];
+#pragma unroll
+    for (int cam = 0; cam < CAM; ++cam)
+      if ((V >> cam) & 1) {
+        const Taps t = decode(rec[cam], kp.fsY, tp.fX, __uint_as_float(rec[cam].y), __uint_as_float(rec[cam].z));
+#pragma unroll
+        for (int k = 0; k < FB; ++k) f[k][cam] = sample4(fc[k], t);
+      }
+    const int nst = kp.C - (cg * kCG + q * 4);  // staged channels >= C are padding
+#pragma unroll
+    for (int k = 0; k < FB; ++k) {
+      fc[k] += kp.fsCg;
+      if (!oc[k].act) continue;
+      float* vcg = oc[k].vcg + (CL ? (long long)cg * kCG : (long long)cg * kCG * csr);
+      if (AGG == MVSGI_AGG_STD) {
+        const F4 o = variance_uniform<CAM, V>(f[k]);
+        store4<CL>(kp, vcg, o, nst, csr);
+        if (kp.validOut != nullptr && cg == 0 && q == 0) kp.validOut[oc[k].validIdx] = (n > 1) ? 1 : 0;
+      } else {  // concat: spherical_sweep.py:52-67, out channel = cam * C + c
+#pragma unroll
+        for (int cam = 0; cam < CAM; ++cam)
+          store4<CL>(kp, vcg + (CL ? (long long)(cam * kp.C) : (long long)(cam * kp.C) * csr), f[k][cam], nst, csr);
       }
     }
+  }
+}
 
-    const int nst = FULLC ? 4 : kp.C - (cg * kCG + q * 4);
-    if (AGG == MVSGI_AGG_STD) {
-      float o[4] = {0.f, 0.f, 0.f, 0.f};
-      if (UNI) {
-        tile_variance_uniform<CAM, (V >= 0 ? V : 0)>(f, o);
-      } else if (need) {
-        const float inv = n == 2 ? 0.5f : (n == 3 ? (1.0f / 3.0f) : 0.25f);
+// One octet of one candidate of one frame with per-lane validity bits v (mask boundaries).
+template <int CAM, bool CL>
+MVSGI_DEV void octet_generic(const SweepKP& kp, const TiledKP& tp, const uint4 (&rec)[CAM], const float* fb, const OutCtx& oc,
+                             uint32_t v, int q, int csr) {
+  const int n = __popc(v);
+  const bool need = oc.act && n > 1;  // spherical_sweep_avg.py:106-111
+  for (int cg = 0; cg < kp.CG; ++cg, fb += kp.fsCg) {
+    F4 f[CAM];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float sm = f[0][i];
-#pragma unroll
-          for (int cam = 1; cam < CAM; ++cam) sm += f[cam][i];
-          const float avg = sm * inv;  // :114
-          float acc = 0.f;
-#pragma unroll
-          for (int cam = 0; cam < CAM; ++cam) {
-            const float dlt = ((v >> cam) & 1u) ? f[cam][i] - avg : 0.0f;  // :119-122
-            acc = fmaf(dlt, dlt, acc);
-          }
-          o[i] = acc * inv;
-        }
+    for (int cam = 0; cam < CAM; ++cam) {
+      const bool ld = need && ((v >> cam) & 1u);
+      if (__any_sync(0xFFFFFFFFu, ld)) {
+        // lanes with nothing to sample read their own (always valid) addresses with zero weights
+        const Taps t = decode(rec[cam], kp.fsY, tp.fX, ld ? __uint_as_float(rec[cam].y) : 0.0f,
+                              ld ? __uint_as_float(rec[cam].z) : 0.0f);
+        f[cam] = sample4(fb, t);
+      } else {
+        f[cam].lo = f[cam].hi = 0ull;
       }
-      if (act) {
-        st_lane<CL>(vcg, o, nst, csr);
-        if (PEERS) {
-          for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(vcg + kp.peerDelta[pr], o, nst, csr);
-        }
-        if (VALID && cg == 0 && q == 0) kp.validOut[validIdx] = (n > 1) ? 1 : 0;
-      }
-    } else {  // concat: spherical_sweep.py:52-67
-      if (act) {
+    }
+    F4 o;
+    o.lo = o.hi = 0ull;
+    if (need) {
+      const float inv = n == 2 ? 0.5f : (n == 3 ? (1.0f / 3.0f) : 0.25f);
+      const f32x2 INV = pk2(inv, inv);
+      F4 sm = f[0];
 #pragma unroll
-        for (int cam = 0; cam < CAM; ++cam) {
-          float* dst = vcg + (CL ? (long long)(cam * kp.C) : (long long)(cam * kp.C) * csr);
-          st_lane<CL>(dst, f[cam], nst, csr);
-          if (PEERS) {
-            for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(dst + kp.peerDelta[pr], f[cam], nst, csr);
-          }
-        }
+      for (int cam = 1; cam < CAM; ++cam) { sm.lo = add2(sm.lo, f[cam].lo); sm.hi = add2(sm.hi, f[cam].hi); }
+      // :114  as an fma with +0 so that ptxas cannot contract the product into the subtraction below (it does contract
+  // mul.rn.f32x2 + sub.rn.f32x2 into FFMA2); sweep_kernel rounds the mean separately, like the reference's tensor ops
+  const f32x2 alo = fma2(sm.lo, INV, 0ull), ahi = fma2(sm.hi, INV, 0ull);
+      F4 acc;
+      acc.lo = acc.hi = 0ull;
+#pragma unroll
+      for (int cam = 0; cam < CAM; ++cam) {
+        const bool on = (v >> cam) & 1u;  // :119-122 masked-out cameras contribute (avg - avg)^2 = 0
+        const f32x2 dlo = on ? sub2(f[cam].lo, alo) : 0ull, dhi = on ? sub2(f[cam].hi, ahi) : 0ull;
+        acc.lo = fma2(dlo, dlo, acc.lo);
+        acc.hi = fma2(dhi, dhi, acc.hi);
       }
+      o.lo = mul2(acc.lo, INV);
+      o.hi = mul2(acc.hi, INV);
+    }
+    if (oc.act) {
+      const int nst = kp.C - (cg * kCG + q * 4);
+      store4<CL>(kp, oc.vcg + (CL ? (long long)cg * kCG : (long long)cg * kCG * csr), o, nst, csr);
+      if (kp.validOut != nullptr && cg == 0 && q == 0) kp.validOut[oc.validIdx] = (n > 1) ? 1 : 0;
     }
   }
 }
 
 // Voxels nobody samples (fewer than two cameras valid): zeros.
-template <bool FULLC, bool VALID, bool PEERS, bool CL>
-MVSGI_DEV void tile_octet_zero(const SweepKP& kp, float* vcg, bool act, int q, int csr, long long validIdx) {
-  const float o[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int cg = 0; cg < kp.CG; ++cg, vcg += (CL ? (long long)kCG : kCG * (long long)csr)) {
-    const int nst = FULLC ? 4 : kp.C - (cg * kCG + q * 4);
-    if (act) {
-      st_lane<CL>(vcg, o, nst, csr);
-      if (PEERS) {
-        for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(vcg + kp.peerDelta[pr], o, nst, csr);
-      }
-      if (VALID && cg == 0 && q == 0) kp.validOut[validIdx] = 0;
-    }
+template <bool CL>
+MVSGI_DEV void octet_zero(const SweepKP& kp, const OutCtx& oc, int q, int csr) {
+  if (!oc.act) return;
+  F4 o;
+  o.lo = o.hi = 0ull;
+  for (int cg = 0; cg < kp.CG; ++cg) {
+    const int nst = kp.C - (cg * kCG + q * 4);
+    store4<CL>(kp, oc.vcg + (CL ? (long long)cg * kCG : (long long)cg * kCG * csr), o, nst, csr);
   }
+  if (kp.validOut != nullptr && q == 0) kp.validOut[oc.validIdx] = 0;
 }
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL>
-__global__ void __launch_bounds__(kTileThreads, 2)
+template <int CAM, int AGG, bool CL, int FB>
+__global__ void __launch_bounds__(kTileThreads, kTileCtas)
 sweep_tiled_kernel(const SweepKP kp, const TiledKP tp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];  // bulk copies need 16-byte aligned destinations
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kTileStages * tp.chunkBytes);
-  uint64_t* empty = full + kTileStages;
-  // per stage: { frame (-1 = no more work), output offset of the tile origin at this candidate, -, - } and the frame's
-  // element offsets into the staged features / the volume as two 64-bit values
-  int4* info = reinterpret_cast<int4*>(empty + kTileStages);
-  longlong2* infoOff = reinterpret_cast<longlong2*>(info + kTileStages);
-
+  __shared__ int sItem[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kTileStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kTileWarps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == kTileWarps) {
-    // ------------------------------------------------------------ producer: item queue + TMA bulk copies of the chunks
-    if (lane != 0) return;
-    int stage = 0, phase = 0;
-    int item = atomicAdd(tp.queue, 1);
-    const int perFrame = tp.numTiles * tp.itemsPerTile;
-    while (item < tp.numItems) {
-      const int next = atomicAdd(tp.queue, 1);  // its latency hides behind this item's copies
-      const int b = item / perFrame, rem = item - b * perFrame;
-      const int tile = rem / tp.itemsPerTile, dg = rem - tile * tp.itemsPerTile;
-      const int ty = tile / tp.tilesX, tx = tile - ty * tp.tilesX;
-      const int d0 = dg * tp.stepsPerItem, d1 = min(kp.D, d0 + tp.stepsPerItem);
-      const unsigned char* src = tp.table + ((size_t)tile * kp.D + d0) * tp.chunkBytes;
-      const int org = ty * tp.tileH * kp.Wo + tx * tp.octPerRow * 8;
-      for (int d = d0; d < d1; ++d, src += tp.chunkBytes) {
-        mbar_wait(&empty[stage], phase ^ 1);  // passes at once the first time round (fresh barrier)
-        info[stage] = make_int4(b, (d + kp.dOff) * kp.Ho * kp.Wo + org, 0, 0);
-        infoOff[stage] = make_longlong2((long long)b * kp.fsB, (long long)b * kp.Cout * kp.Dvol * kp.Ho * kp.Wo);
-        mbar_expect_tx(&full[stage], (uint32_t)tp.chunkBytes);
-        bulk_g2s(smem_raw + (size_t)stage * tp.chunkBytes, src, (uint32_t)tp.chunkBytes, &full[stage]);
-        if (++stage == kTileStages) { stage = 0; phase ^= 1; }
-      }
-      item = next;
-    }
-    mbar_wait(&empty[stage], phase ^ 1);
-    info[stage] = make_int4(-1, 0, 0, 0);
-    mbar_arrive(&full[stage]);
-    return;
-  }
-
-  // -------------------------------------------------------------- consumers: warp = one octet of the tile
-  // (nothing but the ring position is carried from step to step: 56 registers hold one camera's taps in flight)
   const int q = lane & 3, q8 = lane >> 2;
   const int j = warp * 8 + q8;
   const int rowInTile = warp / tp.octPerRow;
   const int poLane = rowInTile * kp.Wo + (warp - rowInTile * tp.octPerRow) * 8 + q8;
-  const int csr = kp.Dvol * kp.Ho * kp.Wo;
-  int stage = 0, phase = 0;
+  const int HW = kp.Ho * kp.Wo;
+  const int csr = kp.Dvol * HW;
+  const long long frameVol = (long long)kp.Cout * csr;
+  const int perGroup = tp.numTiles * tp.itemsPerTile;
 
-  for (;;) {
-    mbar_wait(&full[stage], phase);
-    const int4 in = info[stage];
-    const int b = in.x;
-    if (b < 0) break;
-    const longlong2 offs = infoOff[stage];
-    const float* fb = kp.feat + offs.x + q * 4;  // this lane's row y0 / y0 + 1 pointers into the frame's staged features
-    const float* fb2 = fb + kp.fsY;
-    const unsigned char* chunk = smem_raw + (size_t)stage * tp.chunkBytes;
-    const uint4* rec = reinterpret_cast<const uint4*>(chunk) + j;
-    const uint32_t vin = reinterpret_cast<const uint32_t*>(chunk + tp.vinfoOff)[j];
-    uint32_t v = vin & 0xFu;
-    if (AGG == MVSGI_AGG_STD && kp.perFrameMasks) {  // spherical_sweep_avg.py:92-102, lane q looks up camera q
-      const uint32_t mi = reinterpret_cast<const uint32_t*>(chunk + tp.minfoOff)[j * 4 + q];
-      const uint32_t* mb = kp.mbits + (long long)b * kp.mbB + (q < CAM ? q : 0) * kp.mbCam;
-      const uint32_t bit = mask_eval(mask_fetch(mb, mi, kp.mPitch), mi);
-      const uint32_t ball = __ballot_sync(0xFFFFFFFFu, bit != 0);
-      v = (ball >> (lane & ~3)) & ((1u << CAM) - 1u);
+  if (tid == 0) sItem[0] = atomicAdd(tp.queue, 1);
+  __syncthreads();
+  for (int it = 0;; ++it) {
+    const int item = sItem[it & 1];
+    if (item >= tp.numItems) break;
+    if (tid == 0) sItem[(it + 1) & 1] = atomicAdd(tp.queue, 1);  // its latency hides behind this item
+
+    const int fg = item / perGroup, rem = item - fg * perGroup;
+    const int tile = rem / tp.itemsPerTile, dg = rem - tile * tp.itemsPerTile;
+    const int ty = tile / tp.tilesX, tx = tile - ty * tp.tilesX;
+    const int d0 = dg * tp.stepsPerItem, d1 = min(kp.D, d0 + tp.stepsPerItem);
+    const int org = ty * tp.tileH * kp.Wo + tx * tp.octPerRow * 8 + poLane;
+
+    const float* fb[FB];
+    float* vq[FB];
+    const uint32_t* mb[FB];
+    bool live[FB];
+#pragma unroll
+    for (int k = 0; k < FB; ++k) {
+      const int b = min(fg * FB + k, kp.B - 1);
+      live[k] = fg * FB + k < kp.B;  // the last group of an odd batch repeats its frame without storing it
+      fb[k] = kp.feat + (long long)b * kp.fsB + q * 4;
+      vq[k] = kp.vol + (long long)b * frameVol + (CL ? q * 4 : (long long)q * 4 * csr);
+      mb[k] = kp.mbits + (long long)b * kp.mbB + (q < CAM ? q : 0) * kp.mbCam;
+      // opaque to the compiler: otherwise it re-derives the pointers from the kernel parameters at every tap (a 64-bit
+      // add + shift per load instead of one IMAD.WIDE)
+      asm volatile("" : "+l"(fb[k]), "+l"(vq[k]), "+l"(mb[k]));
     }
-    const bool act = (vin >> 8) & 1u;
-    const int po = in.y + poLane;
-    // host: Cout * Dvol * Ho * Wo < 2^31, so the in-frame part of the offset is 32-bit arithmetic
-    float* vcg = kp.vol + offs.y + (CL ? po * kp.Cout + q * 4 : po + q * 4 * csr);
-    const long long validIdx = VALID ? (long long)b * csr + po : 0;
 
-    if (AGG == MVSGI_AGG_CONCAT) {
-      tile_octet<CAM, AGG, FULLC, VALID, PEERS, CL, (1 << CAM) - 1>(kp, rec, fb, fb2, vcg, v, act, q, q8, csr, validIdx);
-    } else {
-      // warp-uniform validity pattern (the usual case: masks are regions): specialised bodies
-      const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, v, 0);
-      const bool uni = __all_sync(0xFFFFFFFFu, v == v0);
-      if (uni && __popc(v0) < 2) {
-        tile_octet_zero<FULLC, VALID, PEERS, CL>(kp, vcg, act, q, csr, validIdx);
-      } else if (CAM == 3 && uni && v0 == 7u) {
-        tile_octet<CAM, AGG, FULLC, VALID, PEERS, CL, (CAM == 3 ? 7 : -1)>(kp, rec, fb, fb2, vcg, v, act, q, q8, csr, validIdx);
-      } else if (CAM == 3 && uni && v0 == 3u) {
-        tile_octet<CAM, AGG, FULLC, VALID, PEERS, CL, (CAM == 3 ? 3 : -1)>(kp, rec, fb, fb2, vcg, v, act, q, q8, csr, validIdx);
-      } else if (CAM == 3 && uni && v0 == 5u) {
-        tile_octet<CAM, AGG, FULLC, VALID, PEERS, CL, (CAM == 3 ? 5 : -1)>(kp, rec, fb, fb2, vcg, v, act, q, q8, csr, validIdx);
-      } else if (CAM == 3 && uni && v0 == 6u) {
-        tile_octet<CAM, AGG, FULLC, VALID, PEERS, CL, (CAM == 3 ? 6 : -1)>(kp, rec, fb, fb2, vcg, v, act, q, q8, csr, validIdx);
-      } else if (CAM == 4 && uni && v0 == 15u) {
-        tile_octet<CAM, AGG, FULLC, VALID, PEERS, CL, (CAM == 4 ? 15 : -1)>(kp, rec, fb, fb2, vcg, v, act, q, q8, csr, validIdx);
-      } else if (CAM == 2 && uni && v0 == 3u) {
-        tile_octet<CAM, AGG, FULLC, VALID, PEERS, CL, (CAM == 2 ? 3 : -1)>(kp, rec, fb, fb2, vcg, v, act, q, q8, csr, validIdx);
+    const unsigned char* chunk = tp.table + ((size_t)tile * kp.D + d0) * tp.chunkBytes;
+    for (int d = d0; d < d1; ++d, chunk += tp.chunkBytes) {
+      uint4 rec[CAM];
+#pragma unroll
+      for (int cam = 0; cam < CAM; ++cam) rec[cam] = ld_rec(chunk + (size_t)(cam * kTileVox + j) * 16);
+      const uint32_t vin = ld_word(chunk + tp.vinfoOff + j * 4);
+      uint32_t mi = kMaskNone;
+      if (AGG == MVSGI_AGG_STD && kp.perFrameMasks) mi = ld_word(chunk + tp.minfoOff + (j * 4 + q) * 4);
+      if (d + 1 < d1) {  // next candidate's records into L1 while this one's taps are in flight: lane q fetches camera q's line
+        const unsigned char* nchunk = chunk + tp.chunkBytes;
+        if (q < CAM) prefetch_l1(nchunk + (size_t)(q * kTileVox + j) * 16);
+        else prefetch_l1(nchunk + tp.vinfoOff + j * 4);
+        if (AGG == MVSGI_AGG_STD && kp.perFrameMasks && q == 0) prefetch_l1(nchunk + tp.minfoOff + j * 16);
+      }
+
+      const bool inside = (vin >> 8) & 1u;
+      const int po = (d + kp.dOff) * HW + org;
+      OutCtx oc[FB];
+      uint32_t v[FB];
+#pragma unroll
+      for (int k = 0; k < FB; ++k) {
+        oc[k].act = inside && live[k];
+        // host: Cout * Dvol * Ho * Wo < 2^31, so the in-frame part of the offset is 32-bit arithmetic
+        oc[k].vcg = vq[k] + (CL ? (long long)po * kp.Cout : (long long)po);
+        oc[k].validIdx = (long long)min(fg * FB + k, kp.B - 1) * csr + po;
+        v[k] = vin & 0xFu;
+      }
+      if (AGG == MVSGI_AGG_STD && kp.perFrameMasks) {  // spherical_sweep_avg.py:92-102, lane q looks up camera q
+        MaskWords mw[FB];
+#pragma unroll
+        for (int k = 0; k < FB; ++k) mw[k] = mask_fetch(mb[k], mi, kp.mPitch);
+#pragma unroll
+        for (int k = 0; k < FB; ++k) {
+          const uint32_t ball = __ballot_sync(0xFFFFFFFFu, mask_eval(mw[k], mi) != 0);
+          v[k] = (ball >> (lane & ~3)) & ((1u << CAM) - 1u);
+        }
+      }
+
+      if (AGG == MVSGI_AGG_CONCAT) {
+        octet_uniform<CAM, AGG, CL, FB, (1 << CAM) - 1>(kp, tp, rec, fb, oc, q, csr);
       } else {
-        tile_octet<CAM, AGG, FULLC, VALID, PEERS, CL, -1>(kp, rec, fb, fb2, vcg, v, act, q, q8, csr, validIdx);
+        // warp-uniform validity pattern shared by the FB frames (the usual case: masks are regions): specialised bodies
+        const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, v[0], 0);
+        bool same = v[0] == v0;
+#pragma unroll
+        for (int k = 1; k < FB; ++k) same = same && v[k] == v0;
+        const bool uni = __all_sync(0xFFFFFFFFu, same);
+        if (uni && __popc(v0) < 2) {
+#pragma unroll
+          for (int k = 0; k < FB; ++k) octet_zero<CL>(kp, oc[k], q, csr);
+        } else if (CAM == 3 && uni && v0 == 7u) {
+          octet_uniform<CAM, AGG, CL, FB, (CAM == 3 ? 7 : 3)>(kp, tp, rec, fb, oc, q, csr);
+        } else if (CAM == 3 && uni && v0 == 3u) {
+          octet_uniform<CAM, AGG, CL, FB, 3>(kp, tp, rec, fb, oc, q, csr);
+        } else if (CAM == 3 && uni && v0 == 5u) {
+          octet_uniform<CAM, AGG, CL, FB, (CAM == 3 ? 5 : 3)>(kp, tp, rec, fb, oc, q, csr);
+        } else if (CAM == 3 && uni && v0 == 6u) {
+          octet_uniform<CAM, AGG, CL, FB, (CAM == 3 ? 6 : 3)>(kp, tp, rec, fb, oc, q, csr);
+        } else if (CAM == 4 && uni && v0 == 15u) {
+          octet_uniform<CAM, AGG, CL, FB, (CAM == 4 ? 15 : 3)>(kp, tp, rec, fb, oc, q, csr);
+        } else if (CAM == 2 && uni && v0 == 3u) {
+          octet_uniform<CAM, AGG, CL, FB, 3>(kp, tp, rec, fb, oc, q, csr);
+        } else {
+#pragma unroll
+          for (int k = 0; k < FB; ++k)
+            if (live[k]) octet_generic<CAM, CL>(kp, tp, rec, fb[k], oc[k], v[k], q, csr);
+        }
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[stage]);
-    if (++stage == kTileStages) { stage = 0; phase ^= 1; }
+    __syncthreads();  // publishes the next item; keeps the CTA's warps on one tile (their taps share L1 lines)
   }
 }
 

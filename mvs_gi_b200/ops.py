@@ -53,7 +53,7 @@ class SweepCall:
                  rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
                  want_valid: bool = False, out: Optional[Tensor] = None, cand_offset: int = 0,
                  peer_ptrs: Sequence[int] = (), describe_only: bool = False, channels_last: bool = False,
-                 feats_bf16: bool = False, cta_table: bool = False):
+                 feats_bf16: bool = False, cta_table: bool = False, staged_feats: bool = False):
         """`out`, `cand_offset`, `peer_ptrs`: candidate-sharded sweep.  `out` is the full [B, Cout, Dvol, Ho, Wo]
         volume (contiguous); this call fills candidates [cand_offset, cand_offset + num_cands) of it and of every
         peer-mapped volume in `peer_ptrs` (raw device pointers from sharding.PeerVolume).
@@ -62,6 +62,8 @@ class SweepCall:
         `feats_bf16`: stage the features as bfloat16 (MVSGI_FLAG_FEATS_BF16, stated-tolerance mode, fp32 arithmetic).
         `cta_table`: force the CTA-resident-table kernel (MVSGI_FLAG_CTA_TABLE) where the tile-pipelined one would
         run; the two are bit-identical (tests/test_tiled.py) and bench.py times one against the other.
+        `staged_feats`: stage channels-last features into the zero-framed copy instead of tapping them in place
+        (MVSGI_FLAG_STAGED_FEATS; same volume, for tests and bench.py).
         `describe_only`: fill the argument struct (inputs only) without allocating the volume or the workspace —
         how the backward op describes the forward problem to mvsgi_sweep_backward_f32."""
         self.lib = abi.load_library()
@@ -73,7 +75,8 @@ class SweepCall:
         a.struct_size = C.sizeof(abi.MvsgiSweepArgs)
         a.aggregate = aggregate
         self.base_flags = (abi.FLAG_VOL_CHANNELS_LAST if channels_last else 0) | \
-                          (abi.FLAG_FEATS_BF16 if feats_bf16 else 0) | (abi.FLAG_CTA_TABLE if cta_table else 0)
+                          (abi.FLAG_FEATS_BF16 if feats_bf16 else 0) | (abi.FLAG_CTA_TABLE if cta_table else 0) | \
+                          (abi.FLAG_STAGED_FEATS if staged_feats else 0)
         a.flags = self.base_flags
         a.batch, a.num_cams, a.feat_chs, a.num_cands = B, CAM, Cc, num_cands
         a.feat_h, a.feat_w, a.out_h, a.out_w = Hf, Wf, out_h, out_w
