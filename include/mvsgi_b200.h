@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MVSGI_ABI_VERSION 8
+#define MVSGI_ABI_VERSION 9
 #define MVSGI_MAX_CAMS 4
 #define MVSGI_MAX_CANDS 64
 #define MVSGI_MAX_PEERS 7 /* extra destinations of a candidate-sharded sweep (8 GPUs of one box) */
@@ -57,8 +57,13 @@ enum {
   MVSGI_AGG_STD = 0,   /* SphericalSweepStdMasked.sweep  spherical_sweep_avg.py:38-136 */
   MVSGI_AGG_CONCAT = 1 /* SphericalSweep.sweep           spherical_sweep.py:38-68      */
 };
-/* Element type of the masks tensor. */
-enum { MVSGI_MASK_F32 = 0, MVSGI_MASK_U8 = 1 };
+/* Element type of the masks tensor.  MVSGI_MASK_PACKED: `masks` already holds what mvsgi_pack_masks produced for
+ * these images (uint32 words, 8-byte aligned, at least 16 readable bytes after the last image): masks_stride[0] =
+ * words between the image sets of consecutive frames (0 = one set shared by all frames), masks_stride[1] = words
+ * between the cameras of a set (>= (mask_h + 2) * pitch_words * 2), masks_stride[2..3] unused.  The sweep then
+ * launches no packing kernel and reads no float masks: a caller whose masks are static (inference,
+ * api/inference_pytorch.py keeps them on the device) packs them once and pays no mask traffic per call. */
+enum { MVSGI_MASK_F32 = 0, MVSGI_MASK_U8 = 1, MVSGI_MASK_PACKED = 2 };
 /* flags for MvsgiSweepArgs.flags */
 /* Stage the features as bfloat16 (round to nearest even; taps widened back to fp32, all arithmetic in fp32): halves
  * the bytes every tap moves through L1/L2.  Stated-tolerance mode: max|vol - fp32 vol| <= 1e-2 * max|vol|, validity

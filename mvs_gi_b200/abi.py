@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_CAMS = 4
 MAX_CANDS = 64
 MAX_PEERS = 7
@@ -19,7 +19,7 @@ P2P_HANDLE_BYTES = 64
 CAM_EQUIRECT, CAM_DOUBLE_SPHERE, CAM_LINEAR_SPHERE = 0, 1, 2
 GRID_SUPPLIED, GRID_PROJECT = 0, 1
 AGG_STD, AGG_CONCAT = 0, 1
-MASK_F32, MASK_U8 = 0, 1
+MASK_F32, MASK_U8, MASK_PACKED = 0, 1, 2
 FLAG_FEATS_BF16 = 1
 FLAG_STAGE_ONLY = 2
 FLAG_SWEEP_ONLY = 4

@@ -135,8 +135,15 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   if (std_agg) {
     if (a->masks == nullptr) return MVSGI_E_NULL;
     if (a->mask_h < 1 || a->mask_w < 1) return MVSGI_E_SHAPE;
-    if (a->masks_dtype != MVSGI_MASK_F32 && a->masks_dtype != MVSGI_MASK_U8) return MVSGI_E_UNSUPPORTED;
+    if (a->masks_dtype != MVSGI_MASK_F32 && a->masks_dtype != MVSGI_MASK_U8 && a->masks_dtype != MVSGI_MASK_PACKED)
+      return MVSGI_E_UNSUPPORTED;
     if ((int64_t)(a->mask_h + 2) * mask_pitch_words(a->mask_w) * 32 >= (1ll << 28)) return MVSGI_E_SHAPE;
+    if (a->masks_dtype == MVSGI_MASK_PACKED) {  // bits from mvsgi_pack_masks, read as 8-byte row pairs
+      if ((reinterpret_cast<uintptr_t>(a->masks) & 7) != 0 || a->masks_stride[0] % 2 != 0 || a->masks_stride[1] % 2 != 0)
+        return MVSGI_E_STRIDE;
+      if (a->masks_stride[1] < (int64_t)(a->mask_h + 2) * mask_pitch_words(a->mask_w) * 2 || a->masks_stride[0] < 0)
+        return MVSGI_E_STRIDE;
+    }
   }
   if (a->grid_mode == MVSGI_GRID_PROJECT) {
     if (a->rig == nullptr) return MVSGI_E_NULL;
@@ -155,7 +162,7 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
 
   p->cout = std_agg ? a->feat_chs : a->feat_chs * a->num_cams;
   p->cg = (a->feat_chs + mvsgi::kCG - 1) / mvsgi::kCG;
-  p->pack_masks = std_agg;
+  p->pack_masks = std_agg && a->masks_dtype != MVSGI_MASK_PACKED;
   p->per_frame_masks = std_agg && a->batch > 1 && a->masks_stride[0] != 0;
   p->per_frame_grids = a->grid_mode == MVSGI_GRID_SUPPLIED && a->batch > 1 &&
                        (a->grids_stride[0] != 0 || (std_agg && a->grid_masks_stride[0] != 0));
@@ -185,7 +192,7 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   p->feats_bytes = p->direct ? 0
                              : align_up((int64_t)a->batch * a->num_cams * p->cg * (a->feat_h + 3) * (a->feat_w + 2) *
                                             mvsgi::kCG * ((a->flags & MVSGI_FLAG_FEATS_BF16) ? 2 : 4), 256);
-  p->mask_bytes = align_up((int64_t)p->n_mask_images * p->mask_words * 4 + 16, 256);  // +16: funnel-shift over-read
+  p->mask_bytes = p->pack_masks ? align_up((int64_t)p->n_mask_images * p->mask_words * 4 + 16, 256) : 0;  // +16: funnel-shift over-read
   p->flag_bytes = 256;
   p->total_bytes = p->feats_bytes + p->mask_bytes + p->flag_bytes;
 
@@ -317,12 +324,18 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
     kp.direct = 0;
     kp.fX = mvsgi::kCG;
   }
-  if (p.pack_masks) {
-    kp.mbits = ws_bits;
+  if (std_agg) {
     kp.mPitch = p.mask_pitch;
-    kp.mbCam = p.mask_words;
-    kp.mbB = kp.mbCam * a->num_cams;
     kp.perFrameMasks = p.per_frame_masks ? 1 : 0;
+    if (p.pack_masks) {
+      kp.mbits = ws_bits;
+      kp.mbCam = p.mask_words;
+      kp.mbB = kp.mbCam * a->num_cams;
+    } else {  // MVSGI_MASK_PACKED: the caller's bits
+      kp.mbits = (const uint32_t*)a->masks;
+      kp.mbCam = a->masks_stride[1];
+      kp.mbB = a->masks_stride[0];
+    }
   }
   kp.gridMode = a->grid_mode;
   kp.perFrameGrids = p.per_frame_grids ? 1 : 0;

@@ -17,6 +17,7 @@ the reference and keeps its parameter names (`post_vol.conv_layer.weight`,
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Optional, Sequence
 
 import torch
@@ -67,6 +68,13 @@ class _SweepBase(nn.Module):
         self._rig: Optional[Rig] = None
         self._rig_blob: Optional[Tensor] = None
         self._static_masks: Optional[Tensor] = None
+        # Packed mask bits (ops.pack_masks) of the masks tensor last seen, reused while the caller keeps passing the same
+        # tensor object at the same version: inference (api/inference_pytorch.py holds one masks tensor on the device)
+        # then reads no float masks and launches no packing kernel per call.
+        self._mask_cache = None  # (weakref to the masks tensor, its _version, packed bits, (Hm, Wm))
+        # True: every new masks tensor is checked for negative / NaN values when it is packed (one device->host sync per
+        # new tensor; off by default so that a forward stays CUDA-graph capturable); set_static_masks always checks.
+        self.check_masks = False
         # Memory layout of the volume the sweep kernel writes.  False = the reference's NCDHW.  True = the same
         # [B,C,D,Ho,Wo] tensor with torch.channels_last_3d strides: the kernel then stores 512 contiguous bytes per
         # warp and post_vol's Conv3d runs cuDNN's NDHWC path on it.  Values are identical.
@@ -97,7 +105,22 @@ class _SweepBase(nn.Module):
     def set_static_masks(self, masks: Optional[Tensor]) -> "_SweepBase":
         """Inference: masks are the same for every frame ([1|B, CAM, 1, Hm, Wm]); only frame 0 is kept and shared."""
         self._static_masks = None if masks is None else masks[:1].contiguous()
+        self._mask_cache = None
+        if self._static_masks is not None and self._static_masks.is_cuda:
+            self._packed_masks(self._static_masks, check=True)
         return self
+
+    def _packed_masks(self, masks: Tensor, check: bool):
+        """(bits, (Hm, Wm)) for `masks`, packed on first sight of this tensor object / version."""
+        c = self._mask_cache
+        if c is not None and c[0]() is masks and c[1] == masks._version:
+            return c[2], c[3]
+        # an expanded batch of identical masks (stride 0): pack one set
+        src = masks[:1] if (masks.shape[0] > 1 and masks.stride(0) == 0) else masks
+        bits = ops.pack_masks(src, check=check)
+        hw = (int(masks.shape[3]), int(masks.shape[4]))
+        self._mask_cache = (weakref.ref(masks), masks._version, bits, hw)
+        return bits, hw
 
     @classmethod
     def from_reference(cls, module: nn.Module) -> "_SweepBase":
@@ -119,11 +142,18 @@ class _SweepBase(nn.Module):
             grids = grid_masks = None
         else:
             D, Ho, Wo = grids.shape[2:5]
-        if self._aggregate == abi.AGG_STD and self._static_masks is not None:
-            masks = self._static_masks
-        return ops.sweep_op(feats, grids, grid_masks, masks if self._aggregate == abi.AGG_STD else None,
-                            self._rig_blob, self._aggregate, int(Ho), int(Wo), int(D), want_valid,
-                            self.vol_channels_last, self.feats_bf16)
+        mask_h = mask_w = 0
+        if self._aggregate != abi.AGG_STD:
+            masks = None
+        else:
+            if self._static_masks is not None:
+                masks = self._static_masks
+            if masks is None:
+                raise RuntimeError("the std builder needs masks")
+            if masks.is_cuda and masks.dim() == 5 and masks.dtype in (torch.float32, torch.bool, torch.uint8):
+                masks, (mask_h, mask_w) = self._packed_masks(masks, check=self.check_masks)
+        return ops.sweep_op(feats, grids, grid_masks, masks, self._rig_blob, self._aggregate, int(Ho), int(Wo), int(D),
+                            want_valid, self.vol_channels_last, self.feats_bf16, mask_h, mask_w)
 
 
 class SphericalSweepStdMasked(_SweepBase):

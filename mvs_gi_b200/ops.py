@@ -53,15 +53,18 @@ class SweepCall:
                  rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
                  want_valid: bool = False, out: Optional[Tensor] = None, cand_offset: int = 0,
                  peer_ptrs: Sequence[int] = (), describe_only: bool = False, channels_last: bool = False,
-                 feats_bf16: bool = False, cta_table: bool = False, staged_feats: bool = False):
+                 feats_bf16: bool = False, cta_table: bool = False, staged_feats: bool = False,
+                 mask_hw: Optional[Tuple[int, int]] = None):
         """`out`, `cand_offset`, `peer_ptrs`: candidate-sharded sweep.  `out` is the full [B, Cout, Dvol, Ho, Wo]
         volume (contiguous); this call fills candidates [cand_offset, cand_offset + num_cands) of it and of every
         peer-mapped volume in `peer_ptrs` (raw device pointers from sharding.PeerVolume).
         `channels_last`: the volume is a [B, Cout, D, Ho, Wo] tensor with torch.channels_last_3d strides (memory
         [B, D, Ho, Wo, Cout], MVSGI_FLAG_VOL_CHANNELS_LAST) — what post_vol's Conv3d takes without a transpose.
         `feats_bf16`: stage the features as bfloat16 (MVSGI_FLAG_FEATS_BF16, stated-tolerance mode, fp32 arithmetic).
-        `cta_table`: force the CTA-resident-table kernel (MVSGI_FLAG_CTA_TABLE) where the tile-pipelined one would
-        run; the two are bit-identical (tests/test_tiled.py) and bench.py times one against the other.
+        `cta_table`: MVSGI_FLAG_CTA_TABLE (only meaningful in experiment builds of the library, which also hold the
+        tile-walking kernel).
+        `masks` may be the int32 tensor `pack_masks()` returns ([B|1, CAM, words], MVSGI_MASK_PACKED) together with
+        `mask_hw` = (Hm, Wm) of the masks it was packed from: no packing kernel, no float masks read.
         `staged_feats`: stage channels-last features into the zero-framed copy instead of tapping them in place
         (MVSGI_FLAG_STAGED_FEATS; same volume, for tests and bench.py).
         `describe_only`: fill the argument struct (inputs only) without allocating the volume or the workspace —
@@ -89,18 +92,28 @@ class SweepCall:
             if masks is None:
                 raise RuntimeError("the std builder needs masks")
             _require_cuda(masks, "masks")
-            if masks.dim() != 5 or masks.shape[1] != CAM or masks.shape[2] != 1 or masks.shape[0] not in (1, B):
-                raise RuntimeError(f"masks must be [B|1, CAM, 1, Hm, Wm], got {tuple(masks.shape)}")
-            if masks.dtype == torch.float32:
-                a.masks_dtype = abi.MASK_F32
-            elif masks.dtype in (torch.bool, torch.uint8):
-                a.masks_dtype = abi.MASK_U8
+            if masks.dtype == torch.int32:  # bits from pack_masks()
+                if mask_hw is None or masks.dim() != 3 or masks.shape[1] != CAM or masks.shape[0] not in (1, B):
+                    raise RuntimeError("packed masks must be the int32 [B|1, CAM, words] tensor of pack_masks() plus mask_hw")
+                if masks.stride(2) != 1:
+                    raise RuntimeError("packed masks must be contiguous in their last dimension")
+                a.masks_dtype = abi.MASK_PACKED
+                a.mask_h, a.mask_w = int(mask_hw[0]), int(mask_hw[1])
+                a.masks = masks.data_ptr()
+                _fill_strides(a.masks_stride, (0 if masks.shape[0] == 1 else masks.stride(0), masks.stride(1), 0, 0))
             else:
-                raise RuntimeError(f"masks dtype {masks.dtype} not supported (float32, bool, uint8)")
-            a.mask_h, a.mask_w = masks.shape[3], masks.shape[4]
-            a.masks = masks.data_ptr()
-            ms = masks.stride()
-            _fill_strides(a.masks_stride, (0 if masks.shape[0] == 1 else ms[0], ms[1], ms[3], ms[4]))
+                if masks.dim() != 5 or masks.shape[1] != CAM or masks.shape[2] != 1 or masks.shape[0] not in (1, B):
+                    raise RuntimeError(f"masks must be [B|1, CAM, 1, Hm, Wm], got {tuple(masks.shape)}")
+                if masks.dtype == torch.float32:
+                    a.masks_dtype = abi.MASK_F32
+                elif masks.dtype in (torch.bool, torch.uint8):
+                    a.masks_dtype = abi.MASK_U8
+                else:
+                    raise RuntimeError(f"masks dtype {masks.dtype} not supported (float32, bool, uint8)")
+                a.mask_h, a.mask_w = masks.shape[3], masks.shape[4]
+                a.masks = masks.data_ptr()
+                ms = masks.stride()
+                _fill_strides(a.masks_stride, (0 if masks.shape[0] == 1 else ms[0], ms[1], ms[3], ms[4]))
             self.keep.append(masks)
 
         self.rig = None
@@ -197,9 +210,10 @@ class SweepCall:
 
 
 def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                channels_last=False, feats_bf16=False):
+                channels_last=False, feats_bf16=False, mask_h=0, mask_w=0):
     call = SweepCall(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                     channels_last=channels_last, feats_bf16=feats_bf16)
+                     channels_last=channels_last, feats_bf16=feats_bf16,
+                     mask_hw=(mask_h, mask_w) if mask_h > 0 else None)
     call.run()
     # inputs and workspace are only read by kernels already enqueued on this stream; the caching allocator reuses
     # freed blocks in stream order, so dropping the references here is safe.
@@ -209,14 +223,17 @@ def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out
 @torch.library.custom_op("mvsgi::sweep", mutates_args=())
 def sweep_op(feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor], masks: Optional[Tensor],
              rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
-             want_valid: bool, channels_last: bool = False, feats_bf16: bool = False) -> Tuple[Tensor, Tensor]:
+             want_valid: bool, channels_last: bool = False, feats_bf16: bool = False, mask_h: int = 0,
+             mask_w: int = 0) -> Tuple[Tensor, Tensor]:
+    """`masks`: [B|1, CAM, 1, Hm, Wm] float32 / bool / uint8 (reference interface), or the int32 bits of pack_masks()
+    with mask_h, mask_w = the size of the masks they were packed from."""
     return _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                       channels_last, feats_bf16)
+                       channels_last, feats_bf16, mask_h, mask_w)
 
 
 @sweep_op.register_fake
 def _(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid, channels_last=False,
-      feats_bf16=False):
+      feats_bf16=False, mask_h=0, mask_w=0):
     B, CAM, Cc = feats.shape[:3]
     cout = Cc if aggregate == abi.AGG_STD else CAM * Cc
     vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=feats.dtype, device=feats.device,
@@ -268,12 +285,12 @@ def _(costs, inv_dist_idx, out_h, out_w, src_scale, want_norm_costs, want_argmax
 @torch.library.custom_op("mvsgi::sweep_backward", mutates_args=())
 def sweep_backward_op(grad_vol: Tensor, feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor],
                       masks: Optional[Tensor], rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int,
-                      num_cands: int) -> Tensor:
+                      num_cands: int, mask_h: int = 0, mask_w: int = 0) -> Tensor:
     """d sum(grad_vol * sweep(feats, ...)) / d feats  (autograd of spherical_sweep_avg.py:38-136 / spherical_sweep.py:38-68)."""
     lib = abi.load_library()
     _require_cuda(grad_vol, "grad_vol")
     fwd = SweepCall(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands,
-                    describe_only=True)
+                    describe_only=True, mask_hw=(mask_h, mask_w) if mask_h > 0 else None)
     B, CAM, Cc = feats.shape[:3]
     cout = Cc if aggregate == abi.AGG_STD else CAM * Cc
     if tuple(grad_vol.shape) != (B, cout, num_cands, out_h, out_w) or grad_vol.dtype != torch.float32:
@@ -297,14 +314,15 @@ def sweep_backward_op(grad_vol: Tensor, feats: Tensor, grids: Optional[Tensor], 
 
 
 @sweep_backward_op.register_fake
-def _(grad_vol, feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands):
+def _(grad_vol, feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, mask_h=0, mask_w=0):
     return torch.empty_like(feats, memory_format=torch.contiguous_format)
 
 
 def _sweep_setup(ctx, inputs, output):
     feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands = inputs[:9]
     ctx.save_for_backward(feats, grids, grid_masks, masks, rig_blob)
-    ctx.meta = (aggregate, out_h, out_w, num_cands)
+    mask_h, mask_w = (inputs[12], inputs[13]) if len(inputs) > 13 else (0, 0)
+    ctx.meta = (aggregate, out_h, out_w, num_cands, mask_h, mask_w)
 
 
 def _sweep_bwd(ctx, grad_vol, grad_valid):
@@ -312,7 +330,7 @@ def _sweep_bwd(ctx, grad_vol, grad_valid):
     gf = None
     if ctx.needs_input_grad[0] and grad_vol is not None:
         gf = sweep_backward_op(grad_vol, feats, grids, grid_masks, masks, rig_blob, *ctx.meta)
-    return gf, None, None, None, None, None, None, None, None, None, None, None
+    return gf, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 sweep_op.register_autograd(_sweep_bwd, setup_context=_sweep_setup)
@@ -406,6 +424,37 @@ def project_only(rig_struct: abi.MvsgiRig, device) -> Tuple[Tensor, Tensor]:
     with torch.cuda.device(device):
         abi.check(lib.mvsgi_project_only_f32(C.byref(a), _stream_ptr(device)), "mvsgi_project_only_f32")
     return grids, gm.bool().unsqueeze(-1)
+
+
+def pack_masks(masks: Tensor, check: bool = False) -> Tensor:
+    """[N, CAM, 1, Hm, Wm] float32 / bool / uint8 masks -> the int32 [N, CAM, words] bit images the sweep samples
+    (mvsgi_pack_masks; bit set iff mask > 0).  Pass the result as `masks` (with mask_h, mask_w) to sweep_op / SweepCall:
+    masks that do not change between calls are then read exactly once.
+    `check=True` synchronises and raises if a mask value is negative or NaN — for such masks "some positively weighted
+    tap is set" is not the reference's `bilinear(mask) > 0` (spherical_sweep_avg.py:92-96), so they are rejected."""
+    lib = abi.load_library()
+    _require_cuda(masks, "masks")
+    if masks.dim() != 5 or masks.shape[2] != 1:
+        raise RuntimeError(f"masks must be [N, CAM, 1, Hm, Wm], got {tuple(masks.shape)}")
+    if masks.dtype == torch.float32:
+        dt = abi.MASK_F32
+    elif masks.dtype in (torch.bool, torch.uint8):
+        dt = abi.MASK_U8
+    else:
+        raise RuntimeError(f"masks dtype {masks.dtype} not supported (float32, bool, uint8)")
+    N, CAM, _, Hm, Wm = masks.shape
+    words = (Hm + 2) * int(lib.mvsgi_mask_pitch_words(Wm)) * 2
+    # + 4 words: the sweep's funnel shift may read up to 16 bytes past the last image
+    flat = torch.zeros((N * CAM * words + 4,), dtype=torch.int32, device=masks.device)
+    flags = torch.zeros((1,), dtype=torch.int32, device=masks.device)
+    ms = masks.stride()
+    with torch.cuda.device(masks.device):
+        abi.check(lib.mvsgi_pack_masks(masks.data_ptr(), dt, N, ms[0], CAM, ms[1], ms[3], ms[4], Hm, Wm, flat.data_ptr(),
+                                       flags.data_ptr(), _stream_ptr(masks.device)), "mvsgi_pack_masks")
+    if check and int(flags.item()) & 1:
+        raise RuntimeError("mvs_gi_b200: masks hold negative or NaN values; the sweep needs masks >= 0 "
+                           "(the reference's masks are 0/1, multi_view_camera_model_dataset.py:424-438)")
+    return flat[:N * CAM * words].view(N, CAM, words)
 
 
 def launch_counter() -> int:

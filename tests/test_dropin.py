@@ -188,3 +188,48 @@ def test_whole_model_forward_and_backward_through_the_dropins():
                 want = [p.grad for p in host.feature_extractor.parameters()]
                 for a, b in zip(got, want):
                     assert float((a - b).abs().max()) <= 2e-3 * float(b.abs().max()) + 1e-7
+
+
+@pytest.mark.gpu
+def test_masks_are_packed_once_per_tensor_and_checked_on_request():
+    """The module keeps the packed bits of the masks tensor it last saw (same object, same version): a second forward
+    with the same masks launches no packing kernel; an in-place edit or a new tensor re-packs; negative / NaN masks
+    raise when `check_masks` is on (and always through set_static_masks)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mvs_gi_b200 import modules, ops, synthetic
+
+    dev = torch.device("cuda:0")
+    w = synthetic.small(synthetic.WORKLOADS["G16V"], feat_hw=(16, 64), mask_hw=(64, 256), cv_hw=(10, 40), n_cands=4)
+    B = 2
+    feats = torch.from_numpy(synthetic.make_feats(w, B, seed=2)).to(dev)
+    masks = torch.from_numpy(synthetic.erase_rectangles(synthetic.fisheye_footprint_masks(w), B, seed=3)).to(dev)
+    m = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval().attach_rig(w.rig())
+    n0 = ops.launch_counter()
+    v1 = m.sweep(feats, None, None, masks)
+    n1 = ops.launch_counter()
+    v2 = m.sweep(feats, None, None, masks)
+    n2 = ops.launch_counter()
+    assert n1 - n0 == (n2 - n1) + 1, "the second call with the same masks tensor must not pack again"
+    assert torch.equal(v1, v2)
+    masks[0, 1, 0, :, :] = 0.0  # in-place edit bumps the version -> re-pack, different volume
+    v3 = m.sweep(feats, None, None, masks)
+    n3 = ops.launch_counter()
+    assert n3 - n2 == n1 - n0
+    assert not torch.equal(v3, v1)
+    ref = ops.sweep_op(feats, None, None, masks, ops.rig_to_blob(w.rig().to_struct()), 0, *w.cv_hw, 4, False)[0]
+    assert torch.equal(v3, ref), "cached bits == float masks through the op"
+    # expanded (stride-0) batch of one mask set == the set itself
+    one = masks[:1].clone()
+    assert torch.equal(m.sweep(feats, None, None, one.expand(B, -1, -1, -1, -1)), m.sweep(feats, None, None, one))
+    bad = masks.clone()
+    bad[0, 0, 0, 3, 5] = -1.0
+    m.sweep(feats, None, None, bad)  # unchecked by default (no sync, graph-capturable)
+    m.check_masks = True
+    bad2 = bad.clone()
+    with pytest.raises(RuntimeError, match="negative or NaN"):
+        m.sweep(feats, None, None, bad2)
+    nan = masks[:1].clone()
+    nan[0, 0, 0, 0, 0] = float("nan")
+    with pytest.raises(RuntimeError, match="negative or NaN"):
+        m.set_static_masks(nan)
