@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MVSGI_ABI_VERSION 9
+#define MVSGI_ABI_VERSION 10
 #define MVSGI_MAX_CAMS 4
 #define MVSGI_MAX_CANDS 64
 #define MVSGI_MAX_PEERS 7 /* extra destinations of a candidate-sharded sweep (8 GPUs of one box) */
@@ -86,6 +86,13 @@ enum { MVSGI_MASK_F32 = 0, MVSGI_MASK_U8 = 1, MVSGI_MASK_PACKED = 2 };
  * layout (NCHW from cuDNN, odd channel counts) is transposed into the staged copy first.  Same volume bits either way
  * for finite features; the flag exists for tests and bench.py. */
 #define MVSGI_FLAG_STAGED_FEATS 32u
+/* The volume is written as bfloat16 (round to nearest even of the fp32 result; `vol` then points to 2-byte elements):
+ * half the bytes the sweep writes and post_vol's Conv3d re-reads, and the layout + dtype cuDNN's bf16 tensor-core
+ * convolution takes directly (spherical_sweep_avg.py:30-36,165, common_modules.py:82-115).
+ * Stated-tolerance mode: |vol_bf16 - vol| <= 2^-8 * |vol| elementwise, zero pattern unchanged.  Needs
+ * MVSGI_FLAG_VOL_CHANNELS_LAST, feat_chs % 4 == 0 and 8-byte aligned volumes; not available with valid_out, peer_vols
+ * or MVSGI_FLAG_FEATS_BF16; the backward ignores it. */
+#define MVSGI_FLAG_VOL_BF16 64u
 
 /* ---- calibration ------------------------------------------------------- */
 /* One camera the sweep projects into.  rot/trans are the INVERSE pose

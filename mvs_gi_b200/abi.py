@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_CAMS = 4
 MAX_CANDS = 64
 MAX_PEERS = 7
@@ -26,6 +26,7 @@ FLAG_SWEEP_ONLY = 4
 FLAG_VOL_CHANNELS_LAST = 8
 FLAG_CTA_TABLE = 16
 FLAG_STAGED_FEATS = 32
+FLAG_VOL_BF16 = 64
 RESAMPLE_IMG_U8 = 1
 
 LIB_NAME = "libmvsgi_b200.so"

@@ -96,7 +96,12 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   if (a->aggregate != MVSGI_AGG_STD && a->aggregate != MVSGI_AGG_CONCAT) return MVSGI_E_UNSUPPORTED;
   if (a->grid_mode != MVSGI_GRID_SUPPLIED && a->grid_mode != MVSGI_GRID_PROJECT) return MVSGI_E_UNSUPPORTED;
   if (a->flags & ~(MVSGI_FLAG_FEATS_BF16 | MVSGI_FLAG_STAGE_ONLY | MVSGI_FLAG_SWEEP_ONLY | MVSGI_FLAG_VOL_CHANNELS_LAST |
-                   MVSGI_FLAG_CTA_TABLE | MVSGI_FLAG_STAGED_FEATS))
+                   MVSGI_FLAG_CTA_TABLE | MVSGI_FLAG_STAGED_FEATS | MVSGI_FLAG_VOL_BF16))
+    return MVSGI_E_UNSUPPORTED;
+  // bf16 volume: channels-last only, plain forward (no validity output, no peers, fp32 features)
+  if ((a->flags & MVSGI_FLAG_VOL_BF16) &&
+      (!(a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) || (a->flags & MVSGI_FLAG_FEATS_BF16) || a->valid_out != nullptr ||
+       a->num_peers > 0))
     return MVSGI_E_UNSUPPORTED;
   if ((a->flags & MVSGI_FLAG_STAGE_ONLY) && (a->flags & MVSGI_FLAG_SWEEP_ONLY)) return MVSGI_E_UNSUPPORTED;
   // bf16 staging is a plain-forward mode: no validity output, no peer stores
@@ -120,7 +125,7 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   if (cout64 * dvol64 * a->out_h * a->out_w >= (1ll << 31)) return MVSGI_E_SHAPE;
   if (a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) {  // one 16-byte store per lane: 4 whole channels, aligned
     if (a->feat_chs % 4 != 0) return MVSGI_E_SHAPE;
-    if ((reinterpret_cast<uintptr_t>(a->vol) & 15) != 0) return MVSGI_E_STRIDE;
+    if ((reinterpret_cast<uintptr_t>(a->vol) & ((a->flags & MVSGI_FLAG_VOL_BF16) ? 7 : 15)) != 0) return MVSGI_E_STRIDE;
     for (int i = 0; i < a->num_peers; ++i)
       if ((reinterpret_cast<uintptr_t>(a->peer_vols[i]) & 15) != 0) return MVSGI_E_STRIDE;
   }
@@ -352,6 +357,7 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   kp.vol = a->vol;
   kp.volChannelsLast = (a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) ? 1 : 0;
   kp.featsBf16 = (a->flags & MVSGI_FLAG_FEATS_BF16) ? 1 : 0;
+  kp.volBf16 = (a->flags & MVSGI_FLAG_VOL_BF16) ? 1 : 0;
   kp.validOut = std_agg ? a->valid_out : nullptr;
   kp.dOff = a->cand_offset;
   kp.Dvol = a->vol_num_cands > 0 ? a->vol_num_cands : a->num_cands;

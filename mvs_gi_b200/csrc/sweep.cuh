@@ -69,7 +69,7 @@ struct SweepKP {
   uint8_t* validOut;
   // candidate-sharded sweep: the D candidates of this call are candidates [dOff, dOff + D) of a volume with Dvol
   // candidates; every store is repeated at vol + peerDelta[i] (elements) for i < numPeers (peer-mapped volumes)
-  int dOff, Dvol, numPeers, volChannelsLast, featsBf16;
+  int dOff, Dvol, numPeers, volChannelsLast, featsBf16, volBf16;
   long long peerDelta[MVSGI_MAX_PEERS];
 };
 
@@ -226,6 +226,20 @@ MVSGI_DEV void make_entry_direct(const SweepKP& kp, float gx, float gy, int& off
   ly = fsub(y, fy0);
 }
 
+// bfloat16 volume (MVSGI_FLAG_VOL_BF16, channels-last only): the lane's 4 channels are 8 contiguous bytes, rounded to
+// nearest even from the fp32 result.
+template <bool CL>
+MVSGI_DEV void st_lane(uint16_t* p, const float* v, int nst, long long) {
+  if (nst >= 4) {
+    uint32_t lo, hi;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v[3]), "f"(v[2]));
+    asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+  }
+}
+template <bool BF16> struct VolT { typedef float type; };
+template <> struct VolT<true> { typedef uint16_t type; };
+
 // ---- the kernel ---------------------------------------------------------------------------------------------------
 // Shared-memory tap table: one record of kEntryWords(CAM) words per (candidate, pixel) pair
 //   [0] output offset d*Ho*Wo + h*Wo + w   [1] validity bits of the cameras (rewritten per frame if masks are per frame)
@@ -233,7 +247,7 @@ MVSGI_DEV void make_entry_direct(const SweepKP& kp, float gx, float gy, int& off
 // The record stride is odd, so the 8 records a warp reads at a time sit in 8 different banks.
 __host__ __device__ constexpr int entry_words(int cam) { return (2 + 3 * cam) | 1; }
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16, bool DIRECT = false>
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16, bool DIRECT = false, bool VBF16 = false>
 __global__ void __launch_bounds__(kSweepThreads, kSweepCtas)
 sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -370,7 +384,8 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       typedef typename StagedT<BF16>::type FT;  // element type of the staged features (same element offsets)
       const FT* fbq = reinterpret_cast<const FT*>(kp.feat) + (long long)b * kp.fsB + cLane;
       // NCDHW: voxel (c, po) at frame + c*cs + po; channels-last: at frame + po*Cout + c
-      float* vq = kp.vol + (long long)b * kp.Cout * cs + (CL ? (long long)cLane : (long long)cLane * cs);
+      typedef typename VolT<VBF16>::type VT;  // element type of the volume (same element offsets)
+      VT* vq = reinterpret_cast<VT*>(kp.vol) + (long long)b * kp.Cout * cs + (CL ? (long long)cLane : (long long)cLane * cs);
       int fsY = kp.fsY, zeroOff = kp.zeroOff, csr = cs, fX = kp.fX;
       asm volatile("" : "+l"(fbq), "+l"(vq), "+r"(fsY), "+r"(zeroOff), "+r"(csr), "+r"(fX));
 
@@ -385,7 +400,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         const int n = __popc(v);
         const bool need = act && (AGG == MVSGI_AGG_CONCAT || n > 1);  // spherical_sweep_avg.py:106-111
         const FT* fcg = fbq;
-        float* vcg = vq + (CL ? (long long)po * kp.Cout : (long long)po);
+        VT* vcg = vq + (CL ? (long long)po * kp.Cout : (long long)po);
 
         for (int cg = 0; cg < kp.CG; ++cg, fcg += kp.fsCg, vcg += (CL ? (long long)kCG : kCG * (long long)csr)) {
           f32x2 f[CAM][2];  // this lane's 4 channels of every camera's sample, as two packed pairs
@@ -467,7 +482,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
             if (act) {
 #pragma unroll
               for (int cam = 0; cam < CAM; ++cam) {
-                float* dst = vcg + (CL ? (long long)(cam * kp.C) : (long long)(cam * kp.C) * csr);
+                VT* dst = vcg + (CL ? (long long)(cam * kp.C) : (long long)(cam * kp.C) * csr);
                 float fc[4];
                 unpk2(f[cam][0], fc[0], fc[1]);
                 unpk2(f[cam][1], fc[2], fc[3]);

@@ -7,9 +7,10 @@
 namespace mvsgi {
 namespace {
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16 = false, bool DIRECT = false>
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16 = false, bool DIRECT = false,
+          bool VBF16 = false>
 cudaError_t launch_sweep_cl(const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
-  auto kern = sweep_kernel<CAM, AGG, FULLC, VALID, PEERS, CL, BF16, DIRECT>;
+  auto kern = sweep_kernel<CAM, AGG, FULLC, VALID, PEERS, CL, BF16, DIRECT, VBF16>;
   static DynSmemSet smem_set;  // per instantiation
   cudaError_t e = ensure_dyn_smem(kern, smem, smem_set);
   if (e != cudaSuccess) return e;
@@ -30,6 +31,11 @@ template <int CAM, int AGG>
 cudaError_t dispatch_flags(const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem, cudaStream_t st) {
   const bool fullc = kp.C % kCG == 0;
   const bool valid = kp.validOut != nullptr;
+  if (kp.volBf16) {  // validate_and_plan: channels-last volume, no validity output, no peers, fp32 features
+    if (fullc && kp.direct) return launch_sweep_cl<CAM, AGG, true, false, false, true, false, true, true>(kp, rig, grid, smem, st);
+    return fullc ? launch_sweep_cl<CAM, AGG, true, false, false, true, false, false, true>(kp, rig, grid, smem, st)
+                 : launch_sweep_cl<CAM, AGG, false, false, false, true, false, false, true>(kp, rig, grid, smem, st);
+  }
   if (kp.featsBf16) {  // validate_and_plan: no validity output, no peers in this mode
     if (kp.volChannelsLast)
       return fullc ? launch_sweep_cl<CAM, AGG, true, false, false, true, true>(kp, rig, grid, smem, st)

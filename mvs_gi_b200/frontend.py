@@ -25,6 +25,7 @@ from __future__ import annotations
 import json
 import math
 from collections import deque
+from pathlib import Path
 from typing import Dict, List, Mapping, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -246,3 +247,60 @@ def rig_from_manifest(manifest_path, frame_graph, map_cam_frame: Mapping[str, st
             specs[cam_key] = camera_models[sampler["cam_model_key"]]
     return rig_from_calibration(frame_graph, {k: v for k, v in map_cam_frame.items() if k == "cv" or k in specs},
                                 specs, cv_spec, dist_list, extra_transforms)
+
+
+# ---- masks.json -> surrogate validity masks ----------------------------------------------------------------------------
+def read_mask(fn, valid_value: int = 255) -> np.ndarray:
+    """Gray image == valid_value -> bool [H, W]  (mvs_utils/image_io/image_read.py:22-28, cv2.IMREAD_GRAYSCALE)."""
+    try:
+        import cv2
+
+        img = cv2.imread(str(fn), cv2.IMREAD_GRAYSCALE)
+        if img is None:
+            raise FileNotFoundError(f"Failed to read {fn}. ")
+    except ImportError:  # PIL's 'L' conversion equals OpenCV's for single-channel PNGs, which is what masks are
+        from PIL import Image
+
+        img = np.asarray(Image.open(str(fn)).convert("L"))
+    return img == valid_value
+
+
+def read_masks(dataset_path, mask_path="masks.json"):
+    """multi_view_camera_model_dataset.py:223-277: {"masks": [{"raw_camera": "cam0", "mask": "valid_mask_0.png"}, ...],
+    "masks_augmented": [...] (optional)} -> (masks, masks_augmented): dicts raw_camera -> float32 0/1 array [H, W]
+    (masks_augmented is None when the file has no such section)."""
+    root = Path(dataset_path)
+    with open(root / mask_path, "r") as fp:
+        mask_dict = json.load(fp)
+
+    def section(name):
+        return {d["raw_camera"]: read_mask(root / d["mask"]).astype(np.float32) for d in mask_dict[name]}
+
+    return section("masks"), (section("masks_augmented") if "masks_augmented" in mask_dict else None)
+
+
+def sample_masks(masks: Mapping[str, np.ndarray], samplers: Mapping[str, object], device="cuda"):
+    """The surrogate masks the sweep consumes: every raw fisheye mask through its camera's resampler
+    (multi_view_camera_model_dataset.py:424-438): `mask * 255` sampled with invalid value 0, then `> 0 -> 1`.
+    `samplers[cam]` is a mvs_gi_b200.resample.CameraModelRotation (the f4 kernel) or None for cameras that are swept
+    raw (the reference's NoOpSampler: the mask is passed through).  Returns dict cam -> float32 CUDA tensor [1, Hm, Wm]."""
+    import torch
+
+    out = {}
+    for cam, mask in masks.items():
+        m = torch.as_tensor(np.asarray(mask, dtype=np.float32), device=device)[None]  # ToTensor: [1, H, W]
+        sampler = samplers.get(cam)
+        if sampler is not None:
+            m, _ = sampler(m * 255, invalid_pixel_value=0)
+            m = (m > 0).to(torch.float32).squeeze(0)
+        out[cam] = m
+    return out
+
+
+def stack_masks(masks: Mapping[str, object], cam_keys: Optional[Sequence[str]] = None):
+    """dict cam -> [1, Hm, Wm]  ->  [1, CAM, 1, Hm, Wm], cameras in camK order: what `set_static_masks` / the `masks`
+    argument of the sweep modules take (the DataLoader stacks them the same way, :721-731)."""
+    import torch
+
+    keys = list(cam_keys) if cam_keys is not None else sorted(masks, key=lambda k: int(k[3:]))
+    return torch.stack([masks[k] for k in keys], dim=0)[None]

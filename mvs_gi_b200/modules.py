@@ -81,6 +81,8 @@ class _SweepBase(nn.Module):
         self.vol_channels_last = False
         # Stage the features as bfloat16 inside the sweep (fp32 arithmetic): stated-tolerance mode, 1e-2 * max|vol|.
         self.feats_bf16 = False
+        # Write the volume as bfloat16 (channels-last) and run post_vol in bfloat16 on the tensor cores (row f2).
+        self.vol_bf16 = False
 
     # ---- B200-specific configuration (not part of the reference interface) ----
     def attach_rig(self, rig: Optional[Rig]) -> "_SweepBase":
@@ -93,6 +95,19 @@ class _SweepBase(nn.Module):
         """Emit the cost volume channels-last (NDHWC in memory) and keep post_vol's weights in the same format."""
         self.vol_channels_last = bool(on)
         self.post_vol.to(memory_format=torch.channels_last_3d if on else torch.contiguous_format)
+        return self
+
+    def set_vol_bf16(self, on: bool = True) -> "_SweepBase":
+        """Stated-tolerance mode for the hand-off to post_vol: the sweep rounds its fp32 result to
+        bfloat16 on the way out (|vol_bf16 - vol| <= 2^-8 |vol|, zero pattern unchanged), in the channels-last layout, and
+        post_vol (Conv3d + BatchNorm3d + LeakyReLU, common_modules.py:82-115) runs in bfloat16 — half the volume bytes
+        written and re-read, and cuDNN's tensor-core convolution instead of the fp32 one.  forward() returns float32
+        like the reference (one cast of post_vol's output); sweep() returns the bfloat16 volume.  Implies
+        set_vol_channels_last(True)."""
+        self.vol_bf16 = bool(on)
+        if on:
+            self.set_vol_channels_last(True)
+        self.post_vol.to(torch.bfloat16 if on else torch.float32)
         return self
 
     def set_feats_bf16(self, on: bool = True) -> "_SweepBase":
@@ -153,7 +168,8 @@ class _SweepBase(nn.Module):
             if masks.is_cuda and masks.dim() == 5 and masks.dtype in (torch.float32, torch.bool, torch.uint8):
                 masks, (mask_h, mask_w) = self._packed_masks(masks, check=self.check_masks)
         return ops.sweep_op(feats, grids, grid_masks, masks, self._rig_blob, self._aggregate, int(Ho), int(Wo), int(D),
-                            want_valid, self.vol_channels_last, self.feats_bf16, mask_h, mask_w)
+                            want_valid, self.vol_channels_last, self.feats_bf16, mask_h, mask_w,
+                            self.vol_bf16 and not want_valid)
 
 
 class SphericalSweepStdMasked(_SweepBase):
@@ -172,7 +188,8 @@ class SphericalSweepStdMasked(_SweepBase):
         return vol, valid.bool()
 
     def forward(self, feats: Tensor, grids: Tensor, grid_masks: Tensor, masks: Tensor) -> Tensor:
-        return self.post_vol(self.sweep(feats, grids, grid_masks, masks))  # reference :162-167
+        vol = self.post_vol(self.sweep(feats, grids, grid_masks, masks))  # reference :162-167
+        return vol.float() if self.vol_bf16 else vol
 
 
 class SphericalSweep(_SweepBase):
@@ -186,7 +203,8 @@ class SphericalSweep(_SweepBase):
 
     def forward(self, feats: Tensor, grids: Tensor, grid_masks: Tensor, masks: Tensor) -> Tensor:
         # grid_masks is not used; it is here for compatibility (reference :81).
-        return self.post_vol(self.sweep(feats, grids, masks))
+        vol = self.post_vol(self.sweep(feats, grids, masks))
+        return vol.float() if self.vol_bf16 else vol
 
 
 class DistanceRegressorWithFixedCandidates(nn.Module):

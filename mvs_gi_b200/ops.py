@@ -54,7 +54,7 @@ class SweepCall:
                  want_valid: bool = False, out: Optional[Tensor] = None, cand_offset: int = 0,
                  peer_ptrs: Sequence[int] = (), describe_only: bool = False, channels_last: bool = False,
                  feats_bf16: bool = False, cta_table: bool = False, staged_feats: bool = False,
-                 mask_hw: Optional[Tuple[int, int]] = None):
+                 mask_hw: Optional[Tuple[int, int]] = None, vol_bf16: bool = False):
         """`out`, `cand_offset`, `peer_ptrs`: candidate-sharded sweep.  `out` is the full [B, Cout, Dvol, Ho, Wo]
         volume (contiguous); this call fills candidates [cand_offset, cand_offset + num_cands) of it and of every
         peer-mapped volume in `peer_ptrs` (raw device pointers from sharding.PeerVolume).
@@ -67,6 +67,8 @@ class SweepCall:
         `mask_hw` = (Hm, Wm) of the masks it was packed from: no packing kernel, no float masks read.
         `staged_feats`: stage channels-last features into the zero-framed copy instead of tapping them in place
         (MVSGI_FLAG_STAGED_FEATS; same volume, for tests and bench.py).
+        `vol_bf16`: the volume is written as bfloat16 (MVSGI_FLAG_VOL_BF16, needs `channels_last`; stated-tolerance
+        mode for a bf16 post_vol on the tensor cores).
         `describe_only`: fill the argument struct (inputs only) without allocating the volume or the workspace —
         how the backward op describes the forward problem to mvsgi_sweep_backward_f32."""
         self.lib = abi.load_library()
@@ -79,7 +81,9 @@ class SweepCall:
         a.aggregate = aggregate
         self.base_flags = (abi.FLAG_VOL_CHANNELS_LAST if channels_last else 0) | \
                           (abi.FLAG_FEATS_BF16 if feats_bf16 else 0) | (abi.FLAG_CTA_TABLE if cta_table else 0) | \
-                          (abi.FLAG_STAGED_FEATS if staged_feats else 0)
+                          (abi.FLAG_STAGED_FEATS if staged_feats else 0) | (abi.FLAG_VOL_BF16 if vol_bf16 else 0)
+        if vol_bf16 and not channels_last:
+            raise RuntimeError("a bfloat16 volume needs the channels-last layout (channels_last=True)")
         a.flags = self.base_flags
         a.batch, a.num_cams, a.feat_chs, a.num_cands = B, CAM, Cc, num_cands
         a.feat_h, a.feat_w, a.out_h, a.out_w = Hf, Wf, out_h, out_w
@@ -162,11 +166,14 @@ class SweepCall:
         if out is None:
             if cand_offset or len(peer_ptrs):
                 raise RuntimeError("a candidate-sharded sweep needs the full volume passed as `out`")
-            self.vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=torch.float32, device=feats.device,
+            self.vol = torch.empty((B, cout, num_cands, out_h, out_w),
+                                   dtype=torch.bfloat16 if vol_bf16 else torch.float32, device=feats.device,
                                    memory_format=torch.channels_last_3d if channels_last else torch.contiguous_format)
         else:
             _require_cuda(out, "out")
             fmt = torch.channels_last_3d if channels_last else torch.contiguous_format
+            if vol_bf16:
+                raise RuntimeError("a candidate-sharded sweep writes float32 volumes")
             if (out.dtype != torch.float32 or out.dim() != 5 or not out.is_contiguous(memory_format=fmt)
                     or out.shape[0] != B or out.shape[1] != cout or tuple(out.shape[3:]) != (out_h, out_w)):
                 raise RuntimeError(f"`out` must be a float32 [B, {cout}, Dvol, {out_h}, {out_w}] volume, "
@@ -210,10 +217,10 @@ class SweepCall:
 
 
 def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                channels_last=False, feats_bf16=False, mask_h=0, mask_w=0):
+                channels_last=False, feats_bf16=False, mask_h=0, mask_w=0, vol_bf16=False):
     call = SweepCall(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
                      channels_last=channels_last, feats_bf16=feats_bf16,
-                     mask_hw=(mask_h, mask_w) if mask_h > 0 else None)
+                     mask_hw=(mask_h, mask_w) if mask_h > 0 else None, vol_bf16=vol_bf16)
     call.run()
     # inputs and workspace are only read by kernels already enqueued on this stream; the caching allocator reuses
     # freed blocks in stream order, so dropping the references here is safe.
@@ -224,19 +231,20 @@ def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out
 def sweep_op(feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor], masks: Optional[Tensor],
              rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
              want_valid: bool, channels_last: bool = False, feats_bf16: bool = False, mask_h: int = 0,
-             mask_w: int = 0) -> Tuple[Tensor, Tensor]:
+             mask_w: int = 0, vol_bf16: bool = False) -> Tuple[Tensor, Tensor]:
     """`masks`: [B|1, CAM, 1, Hm, Wm] float32 / bool / uint8 (reference interface), or the int32 bits of pack_masks()
     with mask_h, mask_w = the size of the masks they were packed from."""
     return _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                       channels_last, feats_bf16, mask_h, mask_w)
+                       channels_last, feats_bf16, mask_h, mask_w, vol_bf16)
 
 
 @sweep_op.register_fake
 def _(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid, channels_last=False,
-      feats_bf16=False, mask_h=0, mask_w=0):
+      feats_bf16=False, mask_h=0, mask_w=0, vol_bf16=False):
     B, CAM, Cc = feats.shape[:3]
     cout = Cc if aggregate == abi.AGG_STD else CAM * Cc
-    vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=feats.dtype, device=feats.device,
+    vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=torch.bfloat16 if vol_bf16 else feats.dtype,
+                      device=feats.device,
                       memory_format=torch.channels_last_3d if channels_last else torch.contiguous_format)
     valid = feats.new_empty((B, num_cands, out_h, out_w) if (want_valid and aggregate == abi.AGG_STD) else (0,),
                             dtype=torch.uint8)
@@ -329,8 +337,9 @@ def _sweep_bwd(ctx, grad_vol, grad_valid):
     feats, grids, grid_masks, masks, rig_blob = ctx.saved_tensors
     gf = None
     if ctx.needs_input_grad[0] and grad_vol is not None:
+        grad_vol = grad_vol.float()  # a bfloat16 volume (vol_bf16) hands back a bfloat16 gradient
         gf = sweep_backward_op(grad_vol, feats, grids, grid_masks, masks, rig_blob, *ctx.meta)
-    return gf, None, None, None, None, None, None, None, None, None, None, None, None, None
+    return gf, None, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 sweep_op.register_autograd(_sweep_bwd, setup_context=_sweep_setup)

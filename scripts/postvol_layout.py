@@ -49,4 +49,36 @@ for bench in (False, True):
         out[f"{'channels_last_3d' if cl else 'ncdhw'}{'_cudnn_benchmark' if bench else ''}"] = {
             "post_vol_ms": ms_post, "forward_ms": ms_fwd, "rel_err_vs_ncdhw": err,
             "out_channels_last": bool(y.is_contiguous(memory_format=torch.channels_last_3d))}
+# the bfloat16 hand-off (MVSGI_FLAG_VOL_BF16): bf16 channels-last volume, post_vol in bfloat16 on the tensor cores
+for bench in (False, True):
+    torch.backends.cudnn.benchmark = bench
+    m.set_vol_bf16(True)
+    with torch.no_grad():
+        vol = m.sweep(feats, None, None, None)
+        for _ in range(3):
+            y = m.post_vol(vol)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(10):
+            y = m.post_vol(vol)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms_post = ev[0].elapsed_time(ev[1]) / 10
+        ev[0].record()
+        for _ in range(10):
+            y = m(feats, None, None, None)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms_fwd = ev[0].elapsed_time(ev[1]) / 10
+        ev[0].record()
+        for _ in range(10):
+            vol = m.sweep(feats, None, None, None)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms_sweep = ev[0].elapsed_time(ev[1]) / 10
+    m.set_vol_bf16(False)
+    err = float((y.float() - ref).abs().max() / ref.abs().max())
+    out[f"bf16_channels_last_3d{'_cudnn_benchmark' if bench else ''}"] = {
+        "post_vol_ms": ms_post, "forward_ms": ms_fwd, "sweep_ms": ms_sweep, "rel_err_vs_fp32_ncdhw": err}
 print(json.dumps(out))

@@ -812,3 +812,31 @@ def test_softargmin_backward_vs_oracle_and_torch(dev):
         (g4,) = torch.autograd.grad([inv3], c3, [gi3])
         ref4 = orc.softargmin_backward(cn, reg2.inv_dist_idx.cpu().numpy(), scale, True, gi3.cpu().numpy(), None)
         assert relmax(g4.cpu().numpy(), ref4) <= TOL, (D, scale, "inv only")
+
+
+def test_bf16_volume_stated_tolerance(dev):
+    """MVSGI_FLAG_VOL_BF16 (row f2): the bfloat16 channels-last volume is the fp32 volume rounded to nearest even —
+    bit for bit (so |vol_bf16 - vol| <= 2^-8 |vol| and the zero pattern is unchanged) — for NCHW-staged and in-place
+    features; post_vol in bfloat16 stays within 2e-2 * max of the fp32 module."""
+    from mvs_gi_b200 import modules, ops, synthetic
+
+    w = synthetic.small(synthetic.WORKLOADS["G16V"], feat_hw=(32, 128), mask_hw=(128, 512), cv_hw=(20, 80), n_cands=8)
+    B = 2
+    feats = t(synthetic.make_feats(w, B, 51), dev)
+    masks = t(synthetic.erase_rectangles(synthetic.fisheye_footprint_masks(w), B, 52), dev)
+    ref = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval().attach_rig(w.rig())
+    ref.set_vol_channels_last(True)
+    m16 = modules.SphericalSweepStdMasked(w.num_cams, w.feat_chs, 3).to(dev).eval().attach_rig(w.rig())
+    m16.post_vol.load_state_dict(ref.post_vol.state_dict())
+    m16.set_vol_bf16(True)
+    with torch.no_grad():
+        v32 = ref.sweep(feats, None, None, masks)
+        for f in (feats, feats.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)):
+            v16 = m16.sweep(f, None, None, masks)
+            assert v16.dtype == torch.bfloat16 and v16.is_contiguous(memory_format=torch.channels_last_3d)
+            assert torch.equal(v16, v32.to(torch.bfloat16)), "bf16 volume == round-to-nearest-even of the fp32 volume"
+        o32, o16 = ref(feats, None, None, masks), m16(feats, None, None, masks)
+    assert o16.dtype == torch.float32
+    assert float((o16 - o32).abs().max()) <= 2e-2 * float(o32.abs().max())
+    with pytest.raises(RuntimeError):
+        ops.SweepCall(feats, None, None, masks, ops.rig_to_blob(w.rig().to_struct()), 0, *w.cv_hw, 8, vol_bf16=True)
