@@ -64,7 +64,7 @@ struct SweepPlan {
   int mask_pitch, mask_words;
   int cg;                 // 16-channel groups of the staged features
   int64_t feats_bytes, mask_bytes, flag_bytes, total_bytes;
-  int dch, num_chunks, num_runs, run_len, num_items, max_pairs, grid, group_px, interleave;
+  int dch, num_chunks, num_runs, run_len, num_items, max_pairs, grid, group_px, interleave, unit_oct;
   size_t smem_bytes;
   int cout;
   bool walk;              // channels-last volume: sweep_walk.cuh (experiment builds only)
@@ -215,17 +215,42 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   const int64_t per_px = (int64_t)dch * per_pair + 12;
   const int64_t budget = env_int("MVSGI_TABLE_BYTES", ctas_per_sm >= 4 ? 48 * 1024 : (ctas_per_sm == 2 ? 80 * 1024 : 160 * 1024));
   const int num_oct = (P + 7) / 8;
-  int run_oct = (num_oct + grid_target - 1) / grid_target;
-  if ((int64_t)run_oct * 8 * per_px > budget) run_oct = (int)(budget / (8 * per_px));
-  if (run_oct < 1) return MVSGI_E_SHAPE;
-  p->num_runs = (num_oct + run_oct - 1) / run_oct;
-  p->run_len = 8 * ((num_oct + p->num_runs - 1) / p->num_runs);
+  // interleaved runs are dealt in units of `unit` vertically stacked octets when the image divides into them
+  p->interleave = env_int("MVSGI_INTERLEAVE", 1) ? 1 : 0;
+  int unit = env_int("MVSGI_UNIT_OCT", 1);
+  if (unit < 1 || !p->interleave || a->out_w % 8 != 0 || a->out_h % unit != 0) unit = 1;
+  p->unit_oct = unit;
+  const int num_units = unit > 1 ? (a->out_h / unit) * (a->out_w / 8) : num_oct;
+  // one item = (run, candidate chunk) per resident CTA
+  int run_target = grid_target / ((a->num_cands + dch - 1) / dch);
+  if (run_target < 1) run_target = 1;
+  // Whole waves: when the tap table of 1/run_target of the image does not fit the shared-memory budget, every CTA
+  // takes k equal items instead of the grid running one full wave plus a partial one (4 cameras: 2 x 6 octets per CTA
+  // instead of 8 + 8 for a quarter of the CTAs).
+  auto plan_runs = [&](int n_units, int oct_per_unit) {
+    const int64_t cap = budget / ((int64_t)oct_per_unit * 8 * per_px);  // units per run the table can hold
+    if (cap < 1) return 0;
+    for (int k = 1; k <= 64; ++k) {
+      const int ru = (n_units + k * run_target - 1) / (k * run_target);
+      if (ru <= cap) return ru;
+    }
+    return (int)cap;
+  };
+  int run_units = plan_runs(num_units, unit);
+  if (run_units < 1) {
+    if (unit == 1) return MVSGI_E_SHAPE;
+    unit = p->unit_oct = 1;
+    run_units = plan_runs(num_oct, 1);
+    if (run_units < 1) return MVSGI_E_SHAPE;
+  }
+  const int units = unit > 1 ? num_units : num_oct;
+  p->num_runs = (units + run_units - 1) / run_units;
+  p->run_len = 8 * unit * ((units + p->num_runs - 1) / p->num_runs);
   p->dch = dch;
   p->num_chunks = (a->num_cands + dch - 1) / dch;
   p->num_items = p->num_runs * p->num_chunks;
   p->max_pairs = p->run_len * dch;
   p->grid = p->num_items < grid_target ? p->num_items : grid_target;
-  p->interleave = env_int("MVSGI_INTERLEAVE", 1) ? 1 : 0;
   // order of the (candidate, pixel) records inside a run: with interleaved runs one group = the whole run, i.e.
   // candidate-major over all of the run's octets (measured against groups of 8 px: G16V -3.5 %, 4 cameras -19 %,
   // C=48 -11 %, DoubleSphere -16 %, high-D +1 %)
@@ -308,7 +333,7 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   kp.B = a->batch; kp.C = a->feat_chs; kp.D = a->num_cands; kp.Cout = p.cout; kp.CG = p.cg;
   kp.Ho = a->out_h; kp.Wo = a->out_w; kp.Hf = a->feat_h; kp.Wf = a->feat_w; kp.Hm = a->mask_h; kp.Wm = a->mask_w;
   kp.P = a->out_h * a->out_w; kp.numRuns = p.num_runs; kp.runLen = p.run_len; kp.dch = p.dch;
-  kp.numChunks = p.num_chunks; kp.numItems = p.num_items; kp.maxPairs = p.max_pairs; kp.grpPx = p.group_px; kp.interleave = p.interleave;
+  kp.numChunks = p.num_chunks; kp.numItems = p.num_items; kp.maxPairs = p.max_pairs; kp.grpPx = p.group_px; kp.interleave = p.interleave; kp.unitOct = p.unit_oct;
   kp.wL = p.walk ? p.w_len : 0; kp.wSegs = p.walk ? p.w_segs : 0; kp.wNumSeg = p.walk ? p.w_num_seg : 0;
   if (p.direct) {  // the caller's channels-last tensor: element (b, cam, y, x, c) at b*s0 + cam*s1 + y*s3 + x*s4 + c
     kp.feat = a->feats;
@@ -617,6 +642,9 @@ int mvsgi_resample_f32(const MvsgiResampleArgs* a, void* stream) {
   const MvsgiRig& r = *a->rig;
   if (r.num_cams != 1 || r.num_cands != 1 || r.dist[0] != 1.0f) return MVSGI_E_SHAPE;
   if (r.cams[0].model < 0 || r.cams[0].model > MVSGI_CAM_LINEAR_SPHERE) return MVSGI_E_UNSUPPORTED;
+  // an Equirectangular raw image is sampled with border padding by the reference (camera_models.py:633); only the
+  // zero padding of the fisheye models is implemented
+  if (r.cams[0].model == MVSGI_CAM_EQUIRECT) return MVSGI_E_UNSUPPORTED;
   if (a->batch < 1 || a->channels < 1 || a->in_h < 1 || a->in_w < 1 || r.cv_width < 1 || r.cv_height < 1)
     return MVSGI_E_SHAPE;
   if (a->in_h != r.cams[0].height || a->in_w != r.cams[0].width) return MVSGI_E_SHAPE;  // check_input_shape :92-96

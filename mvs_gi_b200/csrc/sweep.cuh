@@ -47,6 +47,7 @@ struct SweepKP {
   int B, C, D, Cout, CG;
   int Ho, Wo, Hf, Wf, Hm, Wm;
   int P, numRuns, runLen, dch, numChunks, numItems, maxPairs, grpPx, interleave;
+  int unitOct;  // interleaved runs are dealt in units of unitOct vertically stacked octets (1 = single octets)
   int wL, wSegs, wNumSeg;  // sweep_walk.cuh: segment length, segments per run, segments in the image
   // staged features: element (b, cam, cg, yp, xp, c) at feat[b*fsB + cam*fsCam + cg*fsCg + yp*fsY + xp*16 + c]
   const float* feat;
@@ -270,14 +271,25 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
     // A run is either a contiguous range of octets or (interleave) every numRuns-th octet: the strided form spreads
     // the expensive image regions (all cameras valid) and the cheap ones (masked out) evenly over the CTAs.
     int p0, npx;
+    const int U = kp.unitOct, octPerRow = kp.Wo >> 3;  // U > 1: host guarantees Wo % 8 == 0 and Ho % U == 0
+    const int numUnits = U > 1 ? (kp.Ho / U) * octPerRow : numOct;
     if (kp.interleave) {
       p0 = 0;
-      npx = 8 * ((numOct - run + kp.numRuns - 1) / kp.numRuns);
+      npx = 8 * U * ((numUnits - run + kp.numRuns - 1) / kp.numRuns);
     } else {
       p0 = 8 * (int)((long long)numOct * run / kp.numRuns);
       npx = min(kp.P, 8 * (int)((long long)numOct * (run + 1) / kp.numRuns)) - p0;
     }
-    auto pixel_of = [&](int p) { return kp.interleave ? 8 * (run + kp.numRuns * (p >> 3)) + (p & 7) : p0 + p; };
+    // U stacked octets share feature rows between them (vertical neighbours sample rows 1.6 apart), and a run's units
+    // are still spread over the image for load balance
+    auto pixel_of = [&](int p) {
+      if (!kp.interleave) return p0 + p;
+      const int k = p >> 3;
+      if (U == 1) return 8 * (run + kp.numRuns * k) + (p & 7);
+      const int u = run + kp.numRuns * (k / U), sub = k - (k / U) * U;
+      const int ur = u / octPerRow, uc = u - ur * octPerRow;
+      return (ur * U + sub) * kp.Wo + uc * 8 + (p & 7);
+    };
     const int d0 = chunk * kp.dch;
     const int dcount = min(kp.dch, kp.D - d0);
     const int npairs = npx * dcount;

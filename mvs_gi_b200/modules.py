@@ -151,6 +151,10 @@ class _SweepBase(nn.Module):
     def _run(self, feats: Tensor, grids, grid_masks, masks, want_valid: bool = False):
         if feats.shape[1] != self.num_cams:
             raise RuntimeError(f"expected {self.num_cams} cameras, feats has {feats.shape[1]}")
+        if feats.dtype in (torch.float16, torch.bfloat16):
+            # under torch.autocast / Lightning precision 16 the extractor emits half tensors; the sweep computes in
+            # float32 like the reference's own sampler does under autocast (grid_sample is on the fp32 list)
+            feats = feats.float()
         if self._rig_blob is not None:
             rig = self._rig
             D, Ho, Wo = rig.num_cands, rig.cv_camera.H, rig.cv_camera.W
@@ -246,6 +250,8 @@ class DistanceRegressorWithFixedCandidates(nn.Module):
         return H, W, 1.0
 
     def regress(self, costs: Tensor, want_norm_costs: bool = True, want_argmax: bool = False):
+        if costs.dtype in (torch.float16, torch.bfloat16):  # autocast: softmax runs in float32 there too
+            costs = costs.float()
         H, W = costs.shape[-2:]
         Ho, Wo, scale = self._out_size(H, W)
         return ops.softargmin_op(costs, self.inv_dist_idx, Ho, Wo, float(scale), want_norm_costs, want_argmax)

@@ -39,6 +39,11 @@ class CameraModelRotation:
         if not isinstance(camera_model_target, cal.EquirectCamera):
             raise TypeError("the target of the resampler is the Equirectangular surrogate "
                             "(configs/dataset/surrogate_models_*.yaml)")
+        if isinstance(camera_model_raw, cal.EquirectCamera):
+            # an Equirectangular RAW image is sampled with border padding in the reference
+            # (padding_mode_if_being_sampled = 'border', camera_models.py:633); the kernel pads with zeros
+            raise TypeError("the resampler takes fisheye raw models (DoubleSphere, LinearSphere); an Equirectangular raw "
+                            "image needs border padding, which is not implemented")
         self.camera_model_raw = camera_model_raw
         self.camera_model_target = camera_model_target
         self.default_invalid_value = default_invalid_value
