@@ -28,6 +28,9 @@ inline cudaError_t ensure_dyn_smem(K kern, size_t smem, DynSmemSet& set) {
 // sweep_cta.cu: the CTA-resident-table sweep (sweep.cuh) — per-frame grids, bf16-staged features, any shape
 cudaError_t launch_sweep_cta(int aggregate, int cams, const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
                              cudaStream_t st);
+// sweep_cta_fb.cu: the same kernel with several frames per pass (kp.framesPerPass > 1)
+cudaError_t launch_sweep_cta_fb(int aggregate, int cams, const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
+                                cudaStream_t st);
 #ifdef MVSGI_EXPERIMENTS
 cudaError_t launch_sweep_walk(int aggregate, int cams, const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
                               cudaStream_t st);

@@ -65,6 +65,7 @@ struct SweepPlan {
   int cg;                 // 16-channel groups of the staged features
   int64_t feats_bytes, mask_bytes, flag_bytes, total_bytes;
   int dch, num_chunks, num_runs, run_len, num_items, max_pairs, grid, group_px, interleave, unit_oct;
+  int cta_fb;             // frames per pass of sweep_kernel (sweep.cuh, sweep_frames_per_pass)
   size_t smem_bytes;
   int cout;
   bool walk;              // channels-last volume: sweep_walk.cuh (experiment builds only)
@@ -203,9 +204,16 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
 
   // Work decomposition (sweep.cuh): equal runs of output pixels, one per resident CTA when the tap table fits.
   const int P = a->out_h * a->out_w;
-  int ctas_per_sm = env_int("MVSGI_CTAS_PER_SM", mvsgi::kSweepCtas);
+  // Several frames per pass (sweep.cuh, FB): static masks and shared grids, so one table record serves every frame;
+  // instantiated for whole channel groups tapped in place into a channels-last volume (the inference path).
+  p->cta_fb = (a->batch >= 2 && !p->per_frame_masks && !p->per_frame_grids && p->direct &&
+               (a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) && a->valid_out == nullptr && a->num_peers == 0 &&
+               env_int("MVSGI_FB_ON", 1) != 0)
+                  ? mvsgi::sweep_frames_per_pass(a->num_cams, a->batch, p->cg) : 1;
+  const int max_ctas = mvsgi::sweep_ctas(p->cta_fb);
+  int ctas_per_sm = env_int("MVSGI_CTAS_PER_SM", max_ctas);
   if (ctas_per_sm < 1) ctas_per_sm = 1;
-  if (ctas_per_sm > mvsgi::kSweepCtas) ctas_per_sm = mvsgi::kSweepCtas;  // __launch_bounds__
+  if (ctas_per_sm > max_ctas) ctas_per_sm = max_ctas;  // __launch_bounds__
   const int grid_target = device_sms() * ctas_per_sm;
   int dch = env_int("MVSGI_DCH", 16);
   if (dch < 1) dch = 1;
@@ -334,6 +342,7 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   kp.Ho = a->out_h; kp.Wo = a->out_w; kp.Hf = a->feat_h; kp.Wf = a->feat_w; kp.Hm = a->mask_h; kp.Wm = a->mask_w;
   kp.P = a->out_h * a->out_w; kp.numRuns = p.num_runs; kp.runLen = p.run_len; kp.dch = p.dch;
   kp.numChunks = p.num_chunks; kp.numItems = p.num_items; kp.maxPairs = p.max_pairs; kp.grpPx = p.group_px; kp.interleave = p.interleave; kp.unitOct = p.unit_oct;
+  kp.framesPerPass = p.cta_fb;
   kp.wL = p.walk ? p.w_len : 0; kp.wSegs = p.walk ? p.w_segs : 0; kp.wNumSeg = p.walk ? p.w_num_seg : 0;
   if (p.direct) {  // the caller's channels-last tensor: element (b, cam, y, x, c) at b*s0 + cam*s1 + y*s3 + x*s4 + c
     kp.feat = a->feats;

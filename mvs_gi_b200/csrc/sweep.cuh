@@ -41,12 +41,25 @@ constexpr int kSweepCtas = 1024 / MVSGI_SWEEP_THREADS;
 constexpr int kSweepThreads = 512;  // 128 quads per CTA
 constexpr int kSweepCtas = 2;
 #endif
+// FB > 1 frames per pass (static masks and shared grids only): one decode of a table record, its addresses and its
+// bilinear weights serves FB frames, whose taps are in flight together; fewer, fatter threads.  Measured shapes
+// (profiles/r2t_fb_variants.jsonl, bit-identical volumes): 2 frames x 384 threads is the best all-round (80 registers);
+// 4 frames x 256 threads (128 registers) wins for <= 3 cameras once the batch amortises the slower table build;
+// 3 frames x 256 threads for 4 cameras (4 frames would spill).
+__host__ __device__ constexpr int sweep_threads(int fb) { return fb == 1 ? kSweepThreads : (fb == 2 ? 384 : 256); }
+__host__ __device__ constexpr int sweep_ctas(int fb) { return fb == 1 ? kSweepCtas : 2; }
+inline int sweep_frames_per_pass(int cams, int batch, int chan_groups) {
+  if (batch < 2) return 1;
+  if (cams == 4) return batch >= 6 ? 3 : 2;
+  return (batch >= 16 && chan_groups == 1) ? 4 : 2;
+}
 constexpr uint32_t kMaskNone = 0u;
 
 struct SweepKP {
   int B, C, D, Cout, CG;
   int Ho, Wo, Hf, Wf, Hm, Wm;
   int P, numRuns, runLen, dch, numChunks, numItems, maxPairs, grpPx, interleave;
+  int framesPerPass;  // the FB instantiation of sweep_kernel: 1, or sweep_frames_per_pass() (static masks, shared grids)
   int unitOct;  // interleaved runs are dealt in units of unitOct vertically stacked octets (1 = single octets)
   int wL, wSegs, wNumSeg;  // sweep_walk.cuh: segment length, segments per run, segments in the image
   // staged features: element (b, cam, cg, yp, xp, c) at feat[b*fsB + cam*fsCam + cg*fsCg + yp*fsY + xp*16 + c]
@@ -248,9 +261,11 @@ template <> struct VolT<true> { typedef uint16_t type; };
 // The record stride is odd, so the 8 records a warp reads at a time sit in 8 different banks.
 __host__ __device__ constexpr int entry_words(int cam) { return (2 + 3 * cam) | 1; }
 
-template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16, bool DIRECT = false, bool VBF16 = false>
-__global__ void __launch_bounds__(kSweepThreads, kSweepCtas)
+template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16, bool DIRECT = false, bool VBF16 = false,
+          int FB = 1>
+__global__ void __launch_bounds__(sweep_threads(FB), sweep_ctas(FB))
 sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
+  constexpr int NT = sweep_threads(FB);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int ES = entry_words(CAM);
   const int MP = kp.maxPairs;
@@ -260,7 +275,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
 
   const int tid = threadIdx.x, lane = tid & 31, q = lane & 3;
   const int warp = tid >> 5;
-  constexpr int nwarps = kSweepThreads >> 5;
+  constexpr int nwarps = NT >> 5;
   const int cLane = q * 4;                       // first of the 4 channels (inside a 16-channel group) this lane owns
   const int HW = kp.Ho * kp.Wo;
   const int cs = kp.Dvol * HW;                   // channel stride of vol (host checks Cout * cs < 2^31)
@@ -298,7 +313,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
     const int gsz = 8 * ((((npx + 7) >> 3) + ngroups - 1) / ngroups);
 
     if (kp.gridMode == MVSGI_GRID_PROJECT) {
-      for (int p = tid; p < npx; p += kSweepThreads) {
+      for (int p = tid; p < npx; p += NT) {
         const int pix = min(pixel_of(p), kp.P - 1);
         float rx, ry, rz;
         cv_ray(rig, pix / kp.Wo, pix % kp.Wo, rx, ry, rz);
@@ -311,7 +326,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
 
     // ---------------------------------------------------------------- build: geometry -> tap table
     auto build = [&](int b) {
-      for (int e = tid; e < CAM * npairs; e += kSweepThreads) {
+      for (int e = tid; e < CAM * npairs; e += NT) {
         const int cam = e / npairs, j = e - cam * npairs;
         const int gi = j / (gsz * dcount);
         const int local = j - gi * gsz * dcount;
@@ -357,7 +372,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
     auto lookup_masks = [&](int b) {
       unsigned char* vb8 = reinterpret_cast<unsigned char*>(tab + 1) + (b & 1);
       const uint32_t* mb = kp.mbits + (kp.perFrameMasks ? (long long)b * kp.mbB : 0);
-      for (int j = tid; j < npairs; j += kSweepThreads) {
+      for (int j = tid; j < npairs; j += NT) {
         uint32_t info[CAM];
         MaskWords m[CAM];
 #pragma unroll
@@ -380,8 +395,9 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       }
     }
 
-    // ---------------------------------------------------------------- sweep: frames outer
-    for (int b = 0; b < kp.B; ++b) {
+    // ---------------------------------------------------------------- sweep: frames outer, FB frames per pass
+    // (FB > 1: host guarantees static masks and shared grids, so the table is the same for every frame)
+    for (int b = 0; b < kp.B; b += FB) {
       if (kp.perFrameGrids) {
         __syncthreads();
         build(b);
@@ -391,15 +407,21 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         lookup_masks(b);
         __syncthreads();
       }
-      // Per-frame lane pointers and loop constants, pinned in registers (the empty asm keeps the compiler from
+      // Per-pass lane pointers and loop constants, pinned in registers (the empty asm keeps the compiler from
       // re-deriving them from the kernel parameters inside the loop).
       typedef typename StagedT<BF16>::type FT;  // element type of the staged features (same element offsets)
       const FT* fbq = reinterpret_cast<const FT*>(kp.feat) + (long long)b * kp.fsB + cLane;
       // NCDHW: voxel (c, po) at frame + c*cs + po; channels-last: at frame + po*Cout + c
       typedef typename VolT<VBF16>::type VT;  // element type of the volume (same element offsets)
-      VT* vq = reinterpret_cast<VT*>(kp.vol) + (long long)b * kp.Cout * cs + (CL ? (long long)cLane : (long long)cLane * cs);
+      const long long volB = (long long)kp.Cout * cs;
+      VT* vq = reinterpret_cast<VT*>(kp.vol) + (long long)b * volB + (CL ? (long long)cLane : (long long)cLane * cs);
       int fsY = kp.fsY, zeroOff = kp.zeroOff, csr = cs, fX = kp.fX;
       asm volatile("" : "+l"(fbq), "+l"(vq), "+r"(fsY), "+r"(zeroOff), "+r"(csr), "+r"(fX));
+      // frames of this pass: the last pass of an odd batch re-samples its last frame and does not store it
+      const int nb = min(FB, kp.B - b);
+      long long fo[FB];
+#pragma unroll
+      for (int fb = 0; fb < FB; ++fb) fo[fb] = (long long)min(fb, nb - 1) * kp.fsB;
 
       const int q8 = lane >> 2;
       const int vsh = (b & 1) * 8;
@@ -415,7 +437,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         VT* vcg = vq + (CL ? (long long)po * kp.Cout : (long long)po);
 
         for (int cg = 0; cg < kp.CG; ++cg, fcg += kp.fsCg, vcg += (CL ? (long long)kCG : kCG * (long long)csr)) {
-          f32x2 f[CAM][2];  // this lane's 4 channels of every camera's sample, as two packed pairs
+          f32x2 f[FB][CAM][2];  // this lane's 4 channels of every camera's sample, as two packed pairs
 #pragma unroll
           for (int cam = 0; cam < CAM; ++cam) {
             const bool ld = need && ((v >> cam) & 1u);
@@ -430,7 +452,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
               float lxe = ld ? lx : 0.0f;
               const FT* t = fcg + off;
               const FT* t1 = t + fsY;
-              float4 ta, tb, tc, td;
+              float4 ta[FB], tb[FB], tc[FB], td[FB];
               if (DIRECT && ((offr & 15) != 0 || fX != kCG)) {
                 // image edges: the padding tap re-reads its real neighbour with weight 0 (make_entry_direct); also the
                 // general pixel pitch (C > 16)
@@ -441,66 +463,85 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
                 if (ym == 2) ly = 0.0f;
                 if (ym) t1 = t;
                 const int dx = xm ? 0 : fX;
-                ta = ldg4(t), tc = ldg4(t + dx), tb = ldg4(t1), td = ldg4(t1 + dx);
+#pragma unroll
+                for (int fb = 0; fb < FB; ++fb) {
+                  const FT* u = t + fo[fb];
+                  const FT* u1 = t1 + fo[fb];
+                  ta[fb] = ldg4(u), tc[fb] = ldg4(u + dx), tb[fb] = ldg4(u1), td[fb] = ldg4(u1 + dx);
+                }
               } else {
-                ta = ldg4(t), tc = ldg4(t + kCG), tb = ldg4(t1), td = ldg4(t1 + kCG);
+#pragma unroll
+                for (int fb = 0; fb < FB; ++fb) {
+                  const FT* u = t + fo[fb];
+                  const FT* u1 = t1 + fo[fb];
+                  ta[fb] = ldg4(u), tc[fb] = ldg4(u + kCG), tb[fb] = ldg4(u1), td[fb] = ldg4(u1 + kCG);
+                }
               }
               const float wa = __fmul_rn(hx, hy), wb = __fmul_rn(hx, ly), wc = __fmul_rn(lxe, hy),
                           wd = __fmul_rn(lxe, ly);  // backports.py:52-55
               // backports.py:86  Ia*wa + Ib*wb + Ic*wc + Id*wd, summed as (column x0) + (column x1), two channels per
               // instruction
               const f32x2 WA = pk2(wa, wa), WB = pk2(wb, wb), WC = pk2(wc, wc), WD = pk2(wd, wd);
-              f[cam][0] = add2(fma2(pk2(tb.x, tb.y), WB, mul2(pk2(ta.x, ta.y), WA)),
-                               fma2(pk2(td.x, td.y), WD, mul2(pk2(tc.x, tc.y), WC)));
-              f[cam][1] = add2(fma2(pk2(tb.z, tb.w), WB, mul2(pk2(ta.z, ta.w), WA)),
-                               fma2(pk2(td.z, td.w), WD, mul2(pk2(tc.z, tc.w), WC)));
+#pragma unroll
+              for (int fb = 0; fb < FB; ++fb) {
+                f[fb][cam][0] = add2(fma2(pk2(tb[fb].x, tb[fb].y), WB, mul2(pk2(ta[fb].x, ta[fb].y), WA)),
+                                     fma2(pk2(td[fb].x, td[fb].y), WD, mul2(pk2(tc[fb].x, tc[fb].y), WC)));
+                f[fb][cam][1] = add2(fma2(pk2(tb[fb].z, tb[fb].w), WB, mul2(pk2(ta[fb].z, ta[fb].w), WA)),
+                                     fma2(pk2(td[fb].z, td[fb].w), WD, mul2(pk2(tc[fb].z, tc[fb].w), WC)));
+              }
             } else {
-              f[cam][0] = f[cam][1] = 0ull;
+#pragma unroll
+              for (int fb = 0; fb < FB; ++fb) f[fb][cam][0] = f[fb][cam][1] = 0ull;
             }
           }
 
           const int nst = FULLC ? 4 : kp.C - (cg * kCG + cLane);  // staged channels >= C are padding
-          if (AGG == MVSGI_AGG_STD) {
-            float o[4] = {0.f, 0.f, 0.f, 0.f};
-            if (need) {
-              const float inv = n == 2 ? 0.5f : (n == 3 ? (1.0f / 3.0f) : 0.25f);
-              const f32x2 INV = pk2(inv, inv);
 #pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                f32x2 s = f[0][i];
+          for (int fb = 0; fb < FB; ++fb) {
+            const bool actf = act && (FB == 1 || fb < nb);
+            VT* vfb = vcg + fb * volB;
+            if (AGG == MVSGI_AGG_STD) {
+              float o[4] = {0.f, 0.f, 0.f, 0.f};
+              if (need) {
+                const float inv = n == 2 ? 0.5f : (n == 3 ? (1.0f / 3.0f) : 0.25f);
+                const f32x2 INV = pk2(inv, inv);
 #pragma unroll
-                for (int cam = 1; cam < CAM; ++cam) s = add2(s, f[cam][i]);
-                // :114  every step rounds on its own, as the reference's separate tensor ops do.  The mean is an fma
-                // with +0: ptxas contracts mul.rn.f32x2 + sub.rn.f32x2 into one FFMA2, which would round once.
-                const f32x2 avg = fma2(s, INV, 0ull);
-                f32x2 acc = 0ull;
+                for (int i = 0; i < 2; ++i) {
+                  f32x2 s = f[fb][0][i];
+#pragma unroll
+                  for (int cam = 1; cam < CAM; ++cam) s = add2(s, f[fb][cam][i]);
+                  // :114  every step rounds on its own, as the reference's separate tensor ops do.  The mean is an fma
+                  // with +0: ptxas contracts mul.rn.f32x2 + sub.rn.f32x2 into one FFMA2, which would round once.
+                  const f32x2 avg = fma2(s, INV, 0ull);
+                  f32x2 acc = 0ull;
+#pragma unroll
+                  for (int cam = 0; cam < CAM; ++cam) {
+                    // :119-122 masked-out cameras contribute (avg-avg)^2 = 0
+                    const f32x2 dlt = ((v >> cam) & 1u) ? sub2(f[fb][cam][i], avg) : 0ull;
+                    acc = fma2(dlt, dlt, acc);
+                  }
+                  unpk2(mul2(acc, INV), o[2 * i], o[2 * i + 1]);
+                }
+              }
+              if (actf) {
+                st_lane<CL>(vfb, o, nst, csr);
+                if (PEERS) {  // the all-gather of the candidate slices, fused: same voxel into every peer's volume
+                  for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(vfb + kp.peerDelta[pr], o, nst, csr);
+                }
+                if (VALID && cg == 0 && q == 0) kp.validOut[(long long)(b + fb) * cs + po] = (n > 1) ? 1 : 0;
+              }
+            } else {  // concat: spherical_sweep.py:52-67, out channel = cam*C + c, masks ignored
+              if (actf) {
 #pragma unroll
                 for (int cam = 0; cam < CAM; ++cam) {
-                  // :119-122 masked-out cameras contribute (avg-avg)^2 = 0
-                  const f32x2 dlt = ((v >> cam) & 1u) ? sub2(f[cam][i], avg) : 0ull;
-                  acc = fma2(dlt, dlt, acc);
-                }
-                unpk2(mul2(acc, INV), o[2 * i], o[2 * i + 1]);
-              }
-            }
-            if (act) {
-              st_lane<CL>(vcg, o, nst, csr);
-              if (PEERS) {  // the all-gather of the candidate slices, fused: same voxel into every peer's volume
-                for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(vcg + kp.peerDelta[pr], o, nst, csr);
-              }
-              if (VALID && cg == 0 && q == 0) kp.validOut[(long long)b * cs + po] = (n > 1) ? 1 : 0;
-            }
-          } else {  // concat: spherical_sweep.py:52-67, out channel = cam*C + c, masks ignored
-            if (act) {
-#pragma unroll
-              for (int cam = 0; cam < CAM; ++cam) {
-                VT* dst = vcg + (CL ? (long long)(cam * kp.C) : (long long)(cam * kp.C) * csr);
-                float fc[4];
-                unpk2(f[cam][0], fc[0], fc[1]);
-                unpk2(f[cam][1], fc[2], fc[3]);
-                st_lane<CL>(dst, fc, nst, csr);
-                if (PEERS) {
-                  for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(dst + kp.peerDelta[pr], fc, nst, csr);
+                  VT* dst = vfb + (CL ? (long long)(cam * kp.C) : (long long)(cam * kp.C) * csr);
+                  float fc[4];
+                  unpk2(f[fb][cam][0], fc[0], fc[1]);
+                  unpk2(f[fb][cam][1], fc[2], fc[3]);
+                  st_lane<CL>(dst, fc, nst, csr);
+                  if (PEERS) {
+                    for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(dst + kp.peerDelta[pr], fc, nst, csr);
+                  }
                 }
               }
             }
@@ -512,8 +553,8 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       // it has finished its taps of this frame, so the lookups' L2 latency hides behind the warps that are still
       // sampling (measured 551 -> 530 us against doing them at the start of the frame).  spherical_sweep_avg.py:92-102
       if (AGG == MVSGI_AGG_STD && kp.perFrameMasks && !kp.perFrameGrids && b + 1 < kp.B) lookup_masks(b + 1);
-      // One barrier per frame: it publishes the next frame's validity bits and keeps the CTA's warps on the same
-      // frame, so a frame's features are fetched into L1 / L2 once, not once per straggler (measured: free-running
+      // One barrier per pass: it publishes the next frame's validity bits and keeps the CTA's warps on the same
+      // frames, so a frame's features are fetched into L1 / L2 once, not once per straggler (measured: free-running
       // warps cost +30 % L2->L1 traffic).
       __syncthreads();
     }

@@ -78,12 +78,18 @@ cudaError_t dispatch_cams(int cams, const SweepKP& kp, const MvsgiRig& rig, int 
 #ifdef MVSGI_EXPERIMENTS
   if (kp.wL > 0) return cams == 3 ? dispatch_walk<3, AGG>(kp, rig, grid, smem, st) : dispatch_walk<4, AGG>(kp, rig, grid, smem, st);
 #endif
+#ifdef MVSGI_BENCH_ONLY  // quick tuning builds: only the std builder with 3 or 4 cameras
+  if (AGG != MVSGI_AGG_STD || cams < 3) return cudaErrorNotSupported;
+  return cams == 3 ? dispatch_flags<3, MVSGI_AGG_STD>(kp, rig, grid, smem, st)
+                   : dispatch_flags<4, MVSGI_AGG_STD>(kp, rig, grid, smem, st);
+#else
   switch (cams) {
     case 1: return dispatch_flags<1, AGG>(kp, rig, grid, smem, st);
     case 2: return dispatch_flags<2, AGG>(kp, rig, grid, smem, st);
     case 3: return dispatch_flags<3, AGG>(kp, rig, grid, smem, st);
     default: return dispatch_flags<4, AGG>(kp, rig, grid, smem, st);
   }
+#endif
 }
 
 
@@ -99,6 +105,7 @@ cudaError_t launch_sweep_walk(int aggregate, int cams, const SweepKP& kp, const 
 
 cudaError_t launch_sweep_cta(int aggregate, int cams, const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
                              cudaStream_t st) {
+  if (kp.framesPerPass > 1) return launch_sweep_cta_fb(aggregate, cams, kp, rig, grid, smem, st);  // sweep_cta_fb.cu
   return aggregate == MVSGI_AGG_STD ? dispatch_cams<MVSGI_AGG_STD>(cams, kp, rig, grid, smem, st)
                                     : dispatch_cams<MVSGI_AGG_CONCAT>(cams, kp, rig, grid, smem, st);
 }

@@ -131,3 +131,51 @@ def test_channels_last_slices_and_odd_channel_counts_fall_back_to_staging(dev):
     c2.run()
     torch.cuda.synchronize()
     assert torch.equal(c1.vol, c2.vol)
+
+
+# Several frames per pass (sweep.cuh, FB = 2 / 3 / 4): chosen by the library for static masks + channels-last features
+# tapped in place + channels-last volume without a validity output.  Asking for the validity output selects the
+# one-frame-per-pass instantiation, so the two volumes must be bit-identical; batches that are not a multiple of FB end
+# on a partial pass.
+FB_CASES = [
+    # name, small() overrides, B (-> FB per sweep_frames_per_pass), aggregate
+    ("G16V", dict(feat_hw=(32, 128), mask_hw=(128, 512), cv_hw=(20, 80), n_cands=16), 2, "std"),      # FB 2
+    ("G16V", dict(feat_hw=(32, 128), mask_hw=(128, 512), cv_hw=(20, 80), n_cands=16), 5, "std"),      # FB 2, tail
+    ("G16V", dict(feat_hw=(17, 70), mask_hw=(40, 130), cv_hw=(9, 37), n_cands=5), 18, "std"),         # FB 4, tail 2
+    ("G16V", dict(feat_hw=(17, 70), mask_hw=(40, 130), cv_hw=(9, 37), n_cands=5), 17, "std"),         # FB 4, tail 1
+    ("4CAM", dict(feat_hw=(32, 128), mask_hw=(128, 512), cv_hw=(20, 80), n_cands=16), 7, "std"),      # FB 3, tail 1
+    ("4CAM", dict(feat_hw=(16, 64), mask_hw=(64, 256), cv_hw=(10, 40), n_cands=6), 3, "std"),         # FB 2, tail
+    ("G16VV_C48", dict(feat_hw=(16, 64), mask_hw=(64, 256), cv_hw=(10, 40), n_cands=6), 16, "std"),   # 3 groups: FB 2
+    ("G16V_DS", dict(feat_hw=(32, 128), cv_hw=(20, 80), n_cands=5), 16, "std"),                       # FB 4
+    ("G8", dict(feat_hw=(32, 128), cv_hw=(20, 80), n_cands=8), 19, "concat"),                         # FB 4, tail 3
+    ("G8", dict(feat_hw=(5, 9), cv_hw=(9, 37), n_cands=3), 3, "concat"),                              # FB 2, edges
+]
+
+
+@pytest.mark.parametrize("vol_bf16", [False, True])
+@pytest.mark.parametrize("name,kw,B,agg", FB_CASES)
+def test_frames_per_pass_instantiations_are_bit_identical(dev, name, kw, B, agg, vol_bf16):
+    from mvs_gi_b200 import abi, ops, synthetic
+
+    w = synthetic.small(synthetic.WORKLOADS[name], **kw)
+    f = _nhwc(torch.from_numpy(synthetic.make_feats(w, B, seed=21)).to(dev))
+    aggregate = abi.AGG_STD if agg == "std" else abi.AGG_CONCAT
+    masks = torch.from_numpy(synthetic.fisheye_footprint_masks(w)[None]).to(dev) if agg == "std" else None
+    blob = ops.rig_to_blob(w.rig().to_struct())
+
+    def run(**kwargs):
+        call = ops.SweepCall(f, None, None, masks, blob, aggregate, w.cv_hw[0], w.cv_hw[1], len(w.dist_list),
+                             channels_last=True, **kwargs)
+        call.vol.fill_(-7.0)  # a frame the partial pass must not touch twice nor skip
+        call.run()
+        torch.cuda.synchronize()
+        return call.vol
+
+    if vol_bf16:
+        fast = run(vol_bf16=True)
+        ref = run(vol_bf16=True, staged_feats=True)   # staged features: one frame per pass
+    else:
+        fast = run()
+        ref = run(want_valid=True) if agg == "std" else run(staged_feats=True)
+    assert torch.equal(fast, ref), f"max |diff| {float((fast.float() - ref.float()).abs().max())}"
+    assert float(fast.float().abs().max()) > 0
