@@ -397,7 +397,10 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
 
     // ---------------------------------------------------------------- sweep: frames outer, FB frames per pass
     // (FB > 1: host guarantees static masks and shared grids, so the table is the same for every frame)
-    for (int b = 0; b < kp.B; b += FB) {
+    for (int b0 = 0; b0 < kp.B; b0 += FB) {
+      // every pass holds exactly FB frames: the last pass of a batch that is not a multiple of FB starts early and
+      // re-writes the frames it shares with the pass before it (same values); host guarantees B >= FB
+      const int b = FB == 1 ? b0 : min(b0, kp.B - FB);
       if (kp.perFrameGrids) {
         __syncthreads();
         build(b);
@@ -417,11 +420,8 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       VT* vq = reinterpret_cast<VT*>(kp.vol) + (long long)b * volB + (CL ? (long long)cLane : (long long)cLane * cs);
       int fsY = kp.fsY, zeroOff = kp.zeroOff, csr = cs, fX = kp.fX;
       asm volatile("" : "+l"(fbq), "+l"(vq), "+r"(fsY), "+r"(zeroOff), "+r"(csr), "+r"(fX));
-      // frames of this pass: the last pass of an odd batch re-samples its last frame and does not store it
-      const int nb = min(FB, kp.B - b);
-      long long fo[FB];
-#pragma unroll
-      for (int fb = 0; fb < FB; ++fb) fo[fb] = (long long)min(fb, nb - 1) * kp.fsB;
+      long long fsB = kp.fsB;  // frames of a pass are fsB elements apart
+      asm volatile("" : "+l"(fsB));
 
       const int q8 = lane >> 2;
       const int vsh = (b & 1) * 8;
@@ -445,7 +445,11 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
               // lanes with nothing to sample read the all-zero patch with zero weights: no divergence, no predication
               // (DIRECT: their own, always valid, taps with zero weights)
               const int offr = (int)rec[2 + 3 * cam];
+#ifdef MVSGI_ABL_L1TAPS  // ablation build: every tap inside two 16 KB windows (rows y0, y0 + 1) (L1-resident)
+              const int off = (offr & 0xFF0);
+#else
               const int off = DIRECT ? (offr & ~15) : (ld ? offr : zeroOff);
+#endif
               const float lx = __uint_as_float(rec[3 + 3 * cam]);
               float ly = __uint_as_float(rec[4 + 3 * cam]);
               float hx = ld ? 1.0f - lx : 0.0f, hy = 1.0f - ly;
@@ -463,19 +467,17 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
                 if (ym == 2) ly = 0.0f;
                 if (ym) t1 = t;
                 const int dx = xm ? 0 : fX;
+                const FT* u = t;
+                const FT* u1 = t1;
 #pragma unroll
-                for (int fb = 0; fb < FB; ++fb) {
-                  const FT* u = t + fo[fb];
-                  const FT* u1 = t1 + fo[fb];
+                for (int fb = 0; fb < FB; ++fb, u += fsB, u1 += fsB)
                   ta[fb] = ldg4(u), tc[fb] = ldg4(u + dx), tb[fb] = ldg4(u1), td[fb] = ldg4(u1 + dx);
-                }
               } else {
+                const FT* u = t;
+                const FT* u1 = t1;
 #pragma unroll
-                for (int fb = 0; fb < FB; ++fb) {
-                  const FT* u = t + fo[fb];
-                  const FT* u1 = t1 + fo[fb];
+                for (int fb = 0; fb < FB; ++fb, u += fsB, u1 += fsB)
                   ta[fb] = ldg4(u), tc[fb] = ldg4(u + kCG), tb[fb] = ldg4(u1), td[fb] = ldg4(u1 + kCG);
-                }
               }
               const float wa = __fmul_rn(hx, hy), wb = __fmul_rn(hx, ly), wc = __fmul_rn(lxe, hy),
                           wd = __fmul_rn(lxe, ly);  // backports.py:52-55
@@ -498,7 +500,6 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
           const int nst = FULLC ? 4 : kp.C - (cg * kCG + cLane);  // staged channels >= C are padding
 #pragma unroll
           for (int fb = 0; fb < FB; ++fb) {
-            const bool actf = act && (FB == 1 || fb < nb);
             VT* vfb = vcg + fb * volB;
             if (AGG == MVSGI_AGG_STD) {
               float o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -523,7 +524,11 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
                   unpk2(mul2(acc, INV), o[2 * i], o[2 * i + 1]);
                 }
               }
-              if (actf) {
+#ifdef MVSGI_ABL_NOSTORE  // ablation build: only never-true stores (keeps the arithmetic alive)
+              if (act && o[0] == 123.456f) {
+#else
+              if (act) {
+#endif
                 st_lane<CL>(vfb, o, nst, csr);
                 if (PEERS) {  // the all-gather of the candidate slices, fused: same voxel into every peer's volume
                   for (int pr = 0; pr < kp.numPeers; ++pr) st_lane<CL>(vfb + kp.peerDelta[pr], o, nst, csr);
@@ -531,7 +536,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
                 if (VALID && cg == 0 && q == 0) kp.validOut[(long long)(b + fb) * cs + po] = (n > 1) ? 1 : 0;
               }
             } else {  // concat: spherical_sweep.py:52-67, out channel = cam*C + c, masks ignored
-              if (actf) {
+              if (act) {
 #pragma unroll
                 for (int cam = 0; cam < CAM; ++cam) {
                   VT* dst = vfb + (CL ? (long long)(cam * kp.C) : (long long)(cam * kp.C) * csr);
@@ -552,7 +557,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       // Per-frame masks: each warp looks up its share of the NEXT frame's validity bits (other byte of the record) when
       // it has finished its taps of this frame, so the lookups' L2 latency hides behind the warps that are still
       // sampling (measured 551 -> 530 us against doing them at the start of the frame).  spherical_sweep_avg.py:92-102
-      if (AGG == MVSGI_AGG_STD && kp.perFrameMasks && !kp.perFrameGrids && b + 1 < kp.B) lookup_masks(b + 1);
+      if (FB == 1 && AGG == MVSGI_AGG_STD && kp.perFrameMasks && !kp.perFrameGrids && b + 1 < kp.B) lookup_masks(b + 1);
       // One barrier per pass: it publishes the next frame's validity bits and keeps the CTA's warps on the same
       // frames, so a frame's features are fetched into L1 / L2 once, not once per straggler (measured: free-running
       // warps cost +30 % L2->L1 traffic).

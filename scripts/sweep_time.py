@@ -23,6 +23,8 @@ g = torch.Generator(device=dev).manual_seed(7)
 nsets = max(3, int(200e6 // (B * w.num_cams * Hf * Wf * w.feat_chs * 4)) + 1)
 sets = [torch.randn((B, w.num_cams, Hf, Wf, w.feat_chs), device=dev, generator=g).permute(0, 1, 4, 2, 3)
         for _ in range(min(nsets, 8))]
+if os.environ.get("SAMEFRAME"):  # every frame of the batch is the same frame (stride 0): no HBM feature reads after the first
+    sets = [f[:1].expand(B, -1, -1, -1, -1) for f in sets]
 agg = abi.AGG_STD if w.aggregate == "std" else abi.AGG_CONCAT
 calls = [ops.SweepCall(f, None, None, masks if agg == abi.AGG_STD else None, rig_blob, agg, Ho, Wo, len(w.dist_list),
                        channels_last=True, mask_hw=w.mask_hw) for f in sets]
