@@ -845,8 +845,11 @@ int mvsgi_softargmin_f32(const MvsgiSoftArgminArgs* a, void* stream) {
                   a->costs_stride[1] * a->num_cands + a->costs_stride[2] * a->in_h + a->costs_stride[3] * a->in_w < (1ll << 31) &&
                   !env_int("MVSGI_SOFTARGMIN_GENERIC", 0);
   if (x2) {  // configs/base_model.yaml:28-34 (interp_scale_factor 2, pre_interp): one thread per 2x2 output block
-    dim3 grid((a->in_w + 1 + 127) / 128, a->in_h + 1, a->batch);
-    launch_softargmin_x2(kp, grid, st);
+    // input box staged by TMA when the volume fits a tensor map (softargmin_tma.cuh), else pointer-per-load: same bits
+    if (env_int("MVSGI_SOFTARGMIN_TMA", 1) == 0 || !mvsgi::launch_softargmin_x2_tma(kp, st)) {
+      dim3 grid((a->in_w + 1 + 127) / 128, a->in_h + 1, a->batch);
+      launch_softargmin_x2(kp, grid, st);
+    }
   } else {
     int split = a->num_cands <= 16 ? 1 : (a->num_cands <= 32 ? 2 : 4);
     const int forced = env_int("MVSGI_SOFTARGMIN_DSPLIT", 0);
