@@ -247,13 +247,7 @@ unstage_grad_kernel(const float* __restrict__ src, int n1, int C, int CG, int Hf
 }
 
 // ---- soft-argmin backward ------------------------------------------------------------------------------------------
-struct SoftBwdKP {
-  SoftKP f;              // forward problem (costs, strides, sizes, idx)
-  const float* gInv;     // [B, 1, Hout, Wout] or nullptr
-  const float* gNc;      // [B, D, Hout, Wout] or nullptr
-  float* gradCosts;      // element (b, d, y, x) at gB*b + gD*d + gY*y + gX*x
-  long long gB, gD, gY, gX;
-};
+// SoftBwdKP: softargmin.cuh
 
 __global__ void zero_strided4_kernel(float* p, int n0, int n1, int n2, int n3, long long s0, long long s1, long long s2,
                                      long long s3) {

@@ -34,6 +34,9 @@ cudaError_t launch_sweep_cta_fb(int aggregate, int cams, const SweepKP& kp, cons
 // softargmin_tma.cu: scale-factor-2 soft-argmin with the input box staged by TMA; false = not applicable, nothing launched
 struct SoftKP;
 bool launch_softargmin_x2_tma(const SoftKP& kp, cudaStream_t st);
+// softargmin_bwd.cu: gradient of the scale-factor-2 soft-argmin as a gather (no atomics, no zero fill); D <= 16
+struct SoftBwdKP;
+void launch_softargmin_x2_backward(const SoftBwdKP& kb, cudaStream_t st);
 #ifdef MVSGI_EXPERIMENTS
 cudaError_t launch_sweep_walk(int aggregate, int cams, const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
                               cudaStream_t st);

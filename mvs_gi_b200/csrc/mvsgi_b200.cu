@@ -759,6 +759,8 @@ int mvsgi_sweep_backward_f32(const MvsgiSweepBwdArgs* a, void* stream) {
   return (int)cudaGetLastError();
 }
 
+constexpr int kGatherRows = 4;  // softargmin_bwd.cuh: kSbRows
+
 int mvsgi_softargmin_backward_f32(const MvsgiSoftArgminBwdArgs* a, void* stream) {
   if (a == nullptr || a->fwd == nullptr) return MVSGI_E_NULL;
   if (a->struct_size != sizeof(MvsgiSoftArgminBwdArgs)) return MVSGI_E_VERSION;
@@ -781,6 +783,15 @@ int mvsgi_softargmin_backward_f32(const MvsgiSoftArgminBwdArgs* a, void* stream)
   kb.gB = a->grad_costs_stride[0]; kb.gD = a->grad_costs_stride[1]; kb.gY = a->grad_costs_stride[2];
   kb.gX = a->grad_costs_stride[3];
   cudaStream_t st = (cudaStream_t)stream;
+  const bool x2 = kp.interp && f->out_h == 2 * f->in_h && f->out_w == 2 * f->in_w && f->src_scale_h == 0.5f &&
+                  f->src_scale_w == 0.5f && f->num_cands <= 16 && (int64_t)f->out_h * f->out_w < (1ll << 31) &&
+                  f->costs_stride[1] >= 0 && f->costs_stride[2] >= 0 && f->costs_stride[3] >= 0 &&
+                  (f->in_h + kGatherRows - 1) / kGatherRows <= 65535 && !env_int("MVSGI_SOFTARGMIN_BWD_ATOMIC", 0);
+  if (x2) {  // configs/base_model.yaml:28-34: every input pixel gathers its four 2x2 blocks (softargmin_bwd.cuh)
+    mvsgi::launch_softargmin_x2_backward(kb, st);
+    g_launches++;
+    return (int)cudaGetLastError();
+  }
   if (kp.interp) {  // the upsample's adjoint accumulates with atomics
     const long long total = (long long)kp.B * kp.D * kp.Hin * kp.Win;
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);

@@ -26,6 +26,15 @@ struct SoftKP {
   int* argmax;
 };
 
+// soft-argmin backward (backward.cuh: any scale / candidate count, atomics; softargmin_bwd.cuh: x2 gather)
+struct SoftBwdKP {
+  SoftKP f;              // forward problem (costs, strides, sizes, idx)
+  const float* gInv;     // [B, 1, Hout, Wout] or nullptr
+  const float* gNc;      // [B, D, Hout, Wout] or nullptr
+  float* gradCosts;      // element (b, d, y, x) at gB*b + gD*d + gY*y + gX*x
+  long long gB, gD, gY, gX;
+};
+
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

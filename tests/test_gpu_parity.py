@@ -814,6 +814,32 @@ def test_softargmin_backward_vs_oracle_and_torch(dev):
         assert relmax(g4.cpu().numpy(), ref4) <= TOL, (D, scale, "inv only")
 
 
+@pytest.mark.parametrize("B,D,hw,with_nc", [(2, 16, (80, 320), False), (2, 16, (80, 320), True), (3, 8, (20, 80), True),
+                                            (2, 11, (9, 63), True), (1, 5, (4, 31), False), (2, 16, (5, 32), True),
+                                            (1, 16, (1, 7), True), (1, 16, (6, 1), True)])
+def test_softargmin_backward_gather_kernel_vs_oracle(dev, B, D, hw, with_nc):
+    """The x2 gather kernel (csrc/softargmin_bwd.cuh: no atomics, every input pixel written once) at the full G16V size
+    and at sizes that put tile seams, the clamped last row / column and the lone first row / column everywhere
+    (distance_regressor.py:52-78 through autograd in the reference)."""
+    from mvs_gi_b200 import calibration as cal, modules
+    from oracle import oracle as orc
+
+    reg = modules.DistanceRegressorWithFixedCandidates(96, cal.dist_inverse_spaced(D), 2, True).to(dev)
+    rng = np.random.default_rng(17 * D + hw[0])
+    cn = (rng.standard_normal((B, 1, D, *hw)) * 2.5).astype(np.float32)
+    c = t(cn, dev).requires_grad_(True)
+    inv, nc = reg(c)
+    gi, gn = torch.randn_like(inv), torch.randn_like(nc)
+    (g,) = torch.autograd.grad([inv, nc] if with_nc else [inv], c, [gi, gn] if with_nc else [gi])
+    ref = orc.softargmin_backward(cn, reg.inv_dist_idx.cpu().numpy(), 2, True, gi.cpu().numpy(),
+                                  gn.cpu().numpy() if with_nc else None)
+    assert relmax(g.cpu().numpy(), ref) <= TOL
+    # a gradient buffer that is not zero beforehand must not leak into the result: every element is overwritten
+    (g2,) = torch.autograd.grad([reg(c)[0]], c, [gi])
+    ref2 = orc.softargmin_backward(cn, reg.inv_dist_idx.cpu().numpy(), 2, True, gi.cpu().numpy(), None)
+    assert relmax(g2.cpu().numpy(), ref2) <= TOL
+
+
 def test_bf16_volume_stated_tolerance(dev):
     """MVSGI_FLAG_VOL_BF16 (row f2): the bfloat16 channels-last volume is the fp32 volume rounded to nearest even —
     bit for bit (so |vol_bf16 - vol| <= 2^-8 |vol| and the zero pattern is unchanged) — for NCHW-staged and in-place
