@@ -16,6 +16,8 @@
 // partials).  Borders: block -1 puts all the weight of output row / column 0 on input row / column 0, the last block's
 // two clamped taps land on the same input row / column — expressed as the per-thread weight pairs WY / WX below.
 #pragma once
+#include <cuda.h>
+
 #include "softargmin.cuh"
 #include "sweep.cuh"  // f32x2 helpers
 
@@ -25,11 +27,26 @@ constexpr int kSbRows = 4;                       // input rows per CTA
 constexpr int kSbCols = 31;                      // input columns per CTA
 constexpr int kSbThreads = (kSbRows + 1) * 32;
 
-template <int DREG, bool FULL, bool GNC>  // FULL: D == DREG; GNC: grad_norm_costs present
-__global__ void __launch_bounds__(kSbThreads) softargmin_x2_backward_kernel(const SoftBwdKP kb) {
+// the grad_norm_costs box of a CTA: 2 (kSbRows + 1) output rows x (64 columns + up to 3 of alignment lead), D planes
+constexpr int kSbBoxH = 2 * (kSbRows + 1);
+constexpr int kSbBoxW = 68;
+
+__device__ __forceinline__ uint32_t sb_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// FULL: D == DREG.  GNC: 0 = no grad_norm_costs, 1 = read from global memory (two passes, the second out of L1/L2),
+// 2 = the CTA's box of grad_norm_costs staged in shared memory by one cp.async.bulk.tensor.4d (TMA) that travels while
+// the threads load and interpolate the costs; outside the image the box is zero-filled, which is the gradient there
+template <int DREG, bool FULL, int GNC>
+__global__ void __launch_bounds__(kSbThreads) softargmin_x2_backward_kernel(const SoftBwdKP kb,
+                                                                            const __grid_constant__ CUtensorMap gmap) {
   const SoftKP& kp = kb.f;
+  // dynamic shared memory: xch[kSbRows + 1][DREG][32] (lower-row partials of a warp, for the warp below), then for
+  // GNC == 2 the box gbox[d][kSbBoxH][kSbBoxW]
+  extern __shared__ __align__(128) float dyn[];
+  float (*xch)[DREG][32] = reinterpret_cast<float (*)[DREG][32]>(dyn);
+  float* gbox = dyn + (kSbRows + 1) * DREG * 32;
+  __shared__ __align__(8) unsigned long long mbar;
   __shared__ __align__(8) float2 sidx[DREG];        // every inverse-distance index twice (one LDS.64 = a packed pair)
-  __shared__ float xch[kSbRows + 1][DREG][32];       // lower-row partials of a warp, for the warp below
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int D = FULL ? DREG : kp.D;
@@ -37,9 +54,25 @@ __global__ void __launch_bounds__(kSbThreads) softargmin_x2_backward_kernel(cons
     const float id = (FULL || (int)threadIdx.x < kp.D) ? __ldg(kp.idx + threadIdx.x) : 0.f;
     sidx[threadIdx.x] = make_float2(id, id);
   }
+  if (GNC == 2 && threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sb_smem_addr(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 
   const int b = blockIdx.z;
+  // first output column of the CTA's blocks, and how far it sits past the 16-byte aligned column the box starts at
+  const int gcol0 = 2 * ((int)blockIdx.x * kSbCols - 1) + 1, glead = gcol0 & 3;
+  if (GNC == 2 && threadIdx.x == 0) {
+    const uint32_t mb = sb_smem_addr(&mbar);
+    const uint32_t bytes = (uint32_t)D * kSbBoxH * kSbBoxW * 4;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(sb_smem_addr(gbox)), "l"(reinterpret_cast<unsigned long long>(&gmap)), "r"(mb), "r"(gcol0 - glead),
+        "r"(2 * ((int)blockIdx.y * kSbRows - 1) + 1), "r"(0), "r"(b)
+        : "memory");
+  }
   const int k = blockIdx.y * kSbRows - 1 + w, m = blockIdx.x * kSbCols - 1 + lane;  // this thread's block
   const bool blk = k < kp.Hin && m < kp.Win;
   // forward taps and weights (softargmin_tma.cuh: exact for scale 0.5)
@@ -89,6 +122,18 @@ __global__ void __launch_bounds__(kSbThreads) softargmin_x2_backward_kernel(cons
   const int hw = kp.Hout * kp.Wout;
   constexpr float kLog2e = 1.4426950408889634f;
   const f32x2 LOG2E = pk2(kLog2e, kLog2e);
+  if (GNC == 2) {  // the box has had the whole interpolation to arrive (phase 0 of a barrier used once)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra SB_DONE;\n"
+        "bra SB_WAIT;\n"
+        "SB_DONE:\n"
+        "}\n" ::"r"(sb_smem_addr(&mbar))
+        : "memory");
+  }
   // v[r][d] <- g[r][d] = p_d (G_d - sum_e p_e G_e) for the two pixels of output row r (0 for pixels outside the image)
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -97,10 +142,12 @@ __global__ void __launch_bounds__(kSbThreads) softargmin_x2_backward_kernel(cons
     const float gi0 = (kb.gInv != nullptr && ok0) ? __ldg(kb.gInv + (long long)b * hw + opix) : 0.f;
     const float gi1 = (kb.gInv != nullptr && ok1) ? __ldg(kb.gInv + (long long)b * hw + opix + 1) : 0.f;
     const f32x2 GI = pk2(gi0, gi1);
-    const float* gnc = GNC ? kb.gNc + (long long)b * D * hw + opix : nullptr;
+    const float* gnc = GNC == 1 ? kb.gNc + (long long)b * D * hw + opix : nullptr;
+    const float* gsm = gbox + (2 * w + r) * kSbBoxW + glead + 2 * lane;  // GNC == 2: this block's pair of row r
     auto upstream = [&](int d) {  // G_d of the two pixels
       const f32x2 ID = *reinterpret_cast<const f32x2*>(&sidx[d]);
-      if (!GNC) return mul2(GI, ID);
+      if (GNC == 0) return mul2(GI, ID);
+      if (GNC == 2) return fma2(GI, ID, pk2(gsm[d * (kSbBoxH * kSbBoxW)], gsm[d * (kSbBoxH * kSbBoxW) + 1]));
       const float n0 = ok0 ? __ldg(gnc + (long long)d * hw) : 0.f, n1 = ok1 ? __ldg(gnc + (long long)d * hw + 1) : 0.f;
       return fma2(GI, ID, pk2(n0, n1));
     };

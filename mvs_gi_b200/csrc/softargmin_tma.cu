@@ -1,26 +1,10 @@
 // softargmin_tma.cu — host side of the TMA-staged soft-argmin (softargmin_tma.cuh): tensor map + launch.
 #include "launch.h"
 #include "softargmin_tma.cuh"
+#include "tma_host.h"
 
 namespace mvsgi {
 namespace {
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point table: no link-time dependency on libcuda
-EncodeTiledFn encode_tiled() {
-  static EncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
 
 // resident CTAs per SM of one instantiation x SM count of the current device, looked up once
 template <int DREG, bool FULL, bool NC, bool AM>
@@ -62,21 +46,14 @@ void launch_flags(const SoftKP& kp, const CUtensorMap& tm, const SaTiles& tl, cu
 // aligned base and row / plane / frame pitches); returns false — nothing launched — otherwise, and the caller uses
 // softargmin_x2_kernel (same bits).
 bool launch_softargmin_x2_tma(const SoftKP& kp, cudaStream_t st) {
-  EncodeTiledFn enc = encode_tiled();
-  if (enc == nullptr) return false;
   if (kp.sX != 1 || kp.D > 16 || kp.Win < 2 || kp.Hin < 2) return false;
   if ((reinterpret_cast<uintptr_t>(kp.costs) & 15) != 0) return false;
   const long long sB = kp.B > 1 ? kp.sB : (long long)kp.D * kp.sD;  // the frame pitch is irrelevant for one frame
   if (kp.sY % 4 != 0 || kp.sD % 4 != 0 || sB % 4 != 0 || kp.sY < kp.Win || kp.sD <= 0 || sB <= 0) return false;
   const int dreg = kp.D <= 8 ? 8 : 16;
   CUtensorMap tm;
-  const cuuint64_t gdim[4] = {(cuuint64_t)kp.Win, (cuuint64_t)kp.Hin, (cuuint64_t)kp.D, (cuuint64_t)kp.B};
-  const cuuint64_t gstr[3] = {(cuuint64_t)kp.sY * 4, (cuuint64_t)kp.sD * 4, (cuuint64_t)sB * 4};
-  const cuuint32_t box[4] = {(cuuint32_t)kSaBoxW, (cuuint32_t)kSaBoxH, (cuuint32_t)kp.D, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(kp.costs), gdim, gstr, box, estr,
-          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+  if (!make_map_f32_4d(&tm, kp.costs, kp.Win, kp.Hin, kp.D, kp.B, (cuuint64_t)kp.sY * 4, (cuuint64_t)kp.sD * 4,
+                       (cuuint64_t)sB * 4, kSaBoxW, kSaBoxH, kp.D))
     return false;
   SaTiles tl = {};
   tl.tilesX = (kp.Win + 1 + kSaCols - 1) / kSaCols;
