@@ -12,7 +12,11 @@
  * allocate are the explicit mvsgi_p2p_* helpers at the end of this file.)  Calibration (MvsgiRig) is read
  * from HOST memory at enqueue time and passed to the kernels by value.
  *
- * Threading/streams: re-entrant, no global mutable state.  Work is enqueued on
+ * Threading/streams: re-entrant; calls from several host threads and streams do not
+ * interact.  The only process-wide state is an atomic launch counter
+ * (mvsgi_launch_counter, diagnostics) and write-once caches of device attributes
+ * (SM count, resident CTAs and opt-in shared-memory size per kernel); none of it
+ * changes what a call computes.  Work is enqueued on
  * the stream that is passed in (a cudaStream_t cast to void*); no call
  * synchronises the device, so all of them are safe under CUDA-graph capture.
  *
