@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of an experiment build against the default library.  Usage: bash scripts/gpu_ab.sh <exp-name> <tag>
+# A/B of an experiment build against the default library.  Usage: bash profiles/runners/gpu_ab.sh <exp-name> <tag>
 exp=$1; tag=${2:-ab}
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2

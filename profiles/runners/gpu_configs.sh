@@ -1,5 +1,5 @@
 #!/bin/bash
-# Kernel times of every BASELINE.json configuration (parity cases, not bench lines).  Usage: bash scripts/gpu_configs.sh <tag>
+# Kernel times of every BASELINE.json configuration (parity cases, not bench lines).  Usage: bash profiles/runners/gpu_configs.sh <tag>
 tag=${1:-cfg}
 mkdir -p gpurun_out; : > gpurun_out/configs_$tag.jsonl
 run() {  # workload batch extra...

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU iteration: parity tests, bench line, launch list.  Usage (on the GPU box): bash scripts/gpu_cycle.sh <tag>
+# One GPU iteration: parity tests, bench line, launch list.  Usage (on the GPU box): bash profiles/runners/gpu_cycle.sh <tag>
 tag=${1:-x}
 timeout 300 python -m pytest tests -m gpu -x -q --timeout 60 > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -3 gpurun_out/pytest_gpu_$tag.log
 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_$tag.log 2>&1

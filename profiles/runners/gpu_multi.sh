@@ -1,6 +1,6 @@
 #!/bin/bash
 # Multi-GPU pass (on a box with N GPUs): frame-sharded bench line at N GPUs + candidate-sharded sweep check/timing.
-# Usage: bash scripts/gpu_multi.sh <tag> <N>
+# Usage: bash profiles/runners/gpu_multi.sh <tag> <N>
 tag=${1:-x}; N=${2:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"

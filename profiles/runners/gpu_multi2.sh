@@ -1,6 +1,6 @@
 #!/bin/bash
 # N-GPU pass: frame-sharded bench (weak scaling), candidate-sharded sweep in both volume layouts, 2-GPU parity test.
-# Usage (on an N-GPU box): bash scripts/gpu_multi2.sh <N> <tag>
+# Usage (on an N-GPU box): bash profiles/runners/gpu_multi2.sh <N> <tag>
 N=${1:-2}; tag=${2:-multi}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: bash scripts/gpu_multi_r2.sh N   (under gpurun --gpus N)
+# usage: bash profiles/runners/gpu_multi_r2.sh N   (under gpurun --gpus N)
 N=$1
 mkdir -p gpurun_out
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu --set full captures summarised ON the box (the .ncu-rep files are too large to bring back together); only the
-# sweep report itself is kept.  Usage: bash scripts/gpu_ncu.sh <tag>
+# sweep report itself is kept.  Usage: bash profiles/runners/gpu_ncu.sh <tag>
 tag=${1:-r1h}
 mkdir -p gpurun_out /tmp/rep
 CFG="bench.py default: G16V std, B=32 frames, per-frame float masks, NCHW feats, in-kernel projection, channels-last volume"

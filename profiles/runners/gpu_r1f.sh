@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU pass r1f: parity tests (incl. channels-last volume), bench in both volume layouts, predicated-tap experiment,
-# post_vol layout timing.  Usage (on the GPU box): bash scripts/gpu_r1f.sh
+# post_vol layout timing.  Usage (on the GPU box): bash profiles/runners/gpu_r1f.sh
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q --timeout 180 > gpurun_out/pytest_gpu_r1f.log 2>&1; tail -3 gpurun_out/pytest_gpu_r1f.log
 for lay in ncdhw ndhwc; do

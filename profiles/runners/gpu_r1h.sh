@@ -1,6 +1,6 @@
 #!/bin/bash
 # Final GPU pass of the round (on the GPU box): tests, smoke, bench lines (both arms), launch list, ncu --set full of
-# the sweep / resample / backward kernels, backward + resample measurements.  Usage: bash scripts/gpu_r1h.sh <tag>
+# the sweep / resample / backward kernels, backward + resample measurements.  Usage: bash profiles/runners/gpu_r1h.sh <tag>
 tag=${1:-r1h}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 500 > gpurun_out/clocks_$tag.csv &

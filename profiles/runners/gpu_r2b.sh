@@ -15,4 +15,4 @@ except Exception as e:
     print("tiled $m failed", e, open("gpurun_out/${tag}_tiled_${m}.err").read()[-2000:])
 PY
 done
-bash scripts/gpu_ncu2.sh ${tag}_tiled sweep_tiled_kernel --masks shared | grep -E "duration|hit_rate|wavefronts|inst_executed|issue_active|tex_op_read|warps_active|stalled_long|registers"
+bash profiles/runners/gpu_ncu2.sh ${tag}_tiled sweep_tiled_kernel --masks shared | grep -E "duration|hit_rate|wavefronts|inst_executed|issue_active|tex_op_read|warps_active|stalled_long|registers"

@@ -43,4 +43,4 @@ one w16c1 2 8 nchw shared
 one w8c2 2 8 nchw shared
 one w8c2 1 8 nchw shared
 export MVSGI_B200_LIB=$PWD/mvs_gi_b200/libmvsgi_b200_w8c3.so MVSGI_FRAMES_PER_PASS=1
-bash scripts/gpu_ncu2.sh r2e_w8c3_fb1 sweep_tiled_kernel --masks shared | grep -E "duration|hit_rate|wavefronts|inst_executed|issue_active|tex_op_read|warps_active|stalled_long|registers|xbar2l1|requests"
+bash profiles/runners/gpu_ncu2.sh r2e_w8c3_fb1 sweep_tiled_kernel --masks shared | grep -E "duration|hit_rate|wavefronts|inst_executed|issue_active|tex_op_read|warps_active|stalled_long|registers|xbar2l1|requests"

@@ -22,4 +22,4 @@ done
 one 4CAM 32 cta nhwc per_frame
 one G16VV_C48 16 cta nhwc per_frame
 one G8 32 cta nhwc per_frame
-bash scripts/gpu_ncu2.sh r2g_cta_direct "sweep_kernel" --masks shared --feats-layout nhwc --kernel cta | grep -E "duration|hit_rate|wavefronts|inst_executed|issue_active|tex_op_read|warps_active|stalled_long|registers|xbar2l1|requests|dram"
+bash profiles/runners/gpu_ncu2.sh r2g_cta_direct "sweep_kernel" --masks shared --feats-layout nhwc --kernel cta | grep -E "duration|hit_rate|wavefronts|inst_executed|issue_active|tex_op_read|warps_active|stalled_long|registers|xbar2l1|requests|dram"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Full GPU pass (on the GPU box): parity tests, smoke, bench line (with e2e + cpu baseline), launch list, ncu --set full of
-# the sweep kernel and the soft-argmin kernel.  Usage: bash scripts/gpu_round.sh <tag>
+# the sweep kernel and the soft-argmin kernel.  Usage: bash profiles/runners/gpu_round.sh <tag>
 tag=${1:-x}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 500 > gpurun_out/clocks_$tag.csv &

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 evidence pass: parity tests, smoke, bench line (e2e + cpu baseline + reference on GPU), reference arm, launch
-# list, ncu --set full of the sweep and the soft-argmin kernels.  Usage: bash scripts/gpu_round2.sh <tag>
+# list, ncu --set full of the sweep and the soft-argmin kernels.  Usage: bash profiles/runners/gpu_round2.sh <tag>
 tag=${1:-x}
 mkdir -p gpurun_out /tmp/rep
 timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -3 gpurun_out/pytest_gpu_$tag.log

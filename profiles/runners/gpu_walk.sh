@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU pass: walking-quad sweep (channels-last volume).  Parity tests, then the bench in ndhwc layout with the walker
-# off / on and different segment counts.  Usage (on the GPU box): bash scripts/gpu_walk.sh <tag>
+# off / on and different segment counts.  Usage (on the GPU box): bash profiles/runners/gpu_walk.sh <tag>
 tag=${1:-walk}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q --timeout 180 > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -5 gpurun_out/pytest_gpu_$tag.log
