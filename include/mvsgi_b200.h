@@ -308,9 +308,14 @@ int mvsgi_softargmin_backward_f32(const MvsgiSoftArgminBwdArgs* args, void* cuda
 #define MVSGI_RESAMPLE_IMG_U8 1u /* img holds uint8 pixels; each tap is scaled to [0,1] on load exactly as the CUDA
                                   * `t_imgs.float() / 255.0` of preprocess_imgs (api/inference_pytorch.py:56-57)
                                   * does it: v * float32(1/255) */
+#define MVSGI_RESAMPLE_NEAREST 2u /* interpolation='nearest' of the reference sampler (camera_model_sampler.py:98-120):
+                                   * F.grid_sample(mode='nearest', zeros padding, align_corners=True —
+                                   * planar_as_base.py:127-133): the pixel at nearbyint(((g + 1) / 2) * (size - 1)),
+                                   * 0 outside the image.  The 'blended' mode (:122-163) is three calls and one
+                                   * elementwise combination on the caller's side (mvs_gi_b200/resample.py) */
 typedef struct MvsgiResampleArgs {
   uint32_t struct_size;
-  uint32_t flags;          /* 0 or MVSGI_RESAMPLE_IMG_U8 */
+  uint32_t flags;          /* any of MVSGI_RESAMPLE_IMG_U8, MVSGI_RESAMPLE_NEAREST */
   int32_t batch, channels;
   int32_t in_h, in_w;      /* raw image size; must equal rig->cams[0].height/width */
   const void* img;         /* float32 (or uint8) element (n, c, y, x) at the given ELEMENT strides: an NCHW tensor, or the

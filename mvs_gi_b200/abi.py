@@ -28,6 +28,7 @@ FLAG_CTA_TABLE = 16
 FLAG_STAGED_FEATS = 32
 FLAG_VOL_BF16 = 64
 RESAMPLE_IMG_U8 = 1
+RESAMPLE_NEAREST = 2
 
 LIB_NAME = "libmvsgi_b200.so"
 _PKG_DIR = Path(__file__).resolve().parent

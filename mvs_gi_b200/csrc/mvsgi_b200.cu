@@ -647,7 +647,7 @@ int mvsgi_project_only_f32(const MvsgiProjectArgs* a, void* stream) {
 int mvsgi_resample_f32(const MvsgiResampleArgs* a, void* stream) {
   if (a == nullptr || a->rig == nullptr || a->img == nullptr || a->out == nullptr) return MVSGI_E_NULL;
   if (a->struct_size != sizeof(MvsgiResampleArgs)) return MVSGI_E_VERSION;
-  if (a->flags & ~MVSGI_RESAMPLE_IMG_U8) return MVSGI_E_UNSUPPORTED;
+  if (a->flags & ~(MVSGI_RESAMPLE_IMG_U8 | MVSGI_RESAMPLE_NEAREST)) return MVSGI_E_UNSUPPORTED;
   const MvsgiRig& r = *a->rig;
   if (r.num_cams != 1 || r.num_cands != 1 || r.dist[0] != 1.0f) return MVSGI_E_SHAPE;
   if (r.cams[0].model < 0 || r.cams[0].model > MVSGI_CAM_LINEAR_SPHERE) return MVSGI_E_UNSUPPORTED;
@@ -663,6 +663,7 @@ int mvsgi_resample_f32(const MvsgiResampleArgs* a, void* stream) {
   kp.img = a->img;
   kp.sN = a->img_stride[0]; kp.sC = a->img_stride[1]; kp.sH = a->img_stride[2]; kp.sW = a->img_stride[3];
   kp.invalid = a->invalid_value;
+  kp.nearest = (a->flags & MVSGI_RESAMPLE_NEAREST) ? 1 : 0;
   kp.out = a->out;
   kp.validOut = a->valid_out;
   // the geometry is evaluated once per thread and reused for its images: split the batch over blockIdx.y only as far as

@@ -7,6 +7,7 @@
 //   raw camera point_3d_2_pixel(normalized=True) -> grid                    camera_model_sampler.py:58-64
 //   invalid (raw or target) -> grid = -1, output = invalid value            :67-71, :117
 //   F.grid_sample(bilinear, zeros, align_corners=False)                     :110-114, planar_as_base.py:124-133
+//   interpolation='nearest': F.grid_sample(nearest, zeros, align_corners=True)   :98-120, planar_as_base.py:127-133
 // Here the geometry is evaluated in-kernel from the same MvsgiRig the sweep uses (target model in the cv_* fields,
 // cams[0] = raw model with rot = R_raw_fisheye, trans = 0, one candidate of distance 1), so no grid is read from HBM,
 // and a batch of N images (all cameras sharing a model/orientation, or consecutive frames) is resampled in one launch.
@@ -21,6 +22,7 @@ struct ResampleKP {
   const void* img;     // float32, or uint8 scaled by 1/255 on load (api/inference_pytorch.py:56-57)
   long long sN, sC, sH, sW;
   float invalid;
+  int nearest;         // MVSGI_RESAMPLE_NEAREST
   float* out;          // [N, C, Ht, Wt] contiguous
   uint8_t* validOut;   // [Ht, Wt] or nullptr
 };
@@ -55,6 +57,23 @@ resample_kernel(const ResampleKP kp, const __grid_constant__ MvsgiRig rig) {
   to_camera(rig.cams[0], rx, ry, rz, 1.0f, x, y, z);
   const bool valid = project(rig.cams[0], x, y, z, gx, gy);
   if (kp.validOut != nullptr && blockIdx.y == 0) kp.validOut[pix] = valid ? 1 : 0;
+  if (kp.nearest) {
+    // F.grid_sample(mode='nearest', zeros, align_corners=True): camera_model_sampler.py:98-120, planar_as_base.py:127-133;
+    // ATen: ((g + 1) / 2) * (size - 1), nearbyint (half to even), 0 outside the image (NaN compares false)
+    const float xr = rintf(fmul(fdiv(fadd(gx, 1.0f), 2.0f), (float)(kp.W - 1)));
+    const float yr = rintf(fmul(fdiv(fadd(gy, 1.0f), 2.0f), (float)(kp.H - 1)));
+    const bool inb = valid && xr >= 0.0f && xr <= (float)(kp.W - 1) && yr >= 0.0f && yr <= (float)(kp.H - 1);
+    const long long on = inb ? (long long)(int)yr * kp.sH + (long long)(int)xr * kp.sW : 0;
+    for (int n = blockIdx.y; n < kp.N; n += gridDim.y) {
+      const T* im = static_cast<const T*>(kp.img) + n * kp.sN + on;
+      float* o = kp.out + (long long)n * kp.C * P + pix;
+      for (int c = 0; c < kp.C; ++c) {
+        const float v = valid ? (inb ? ld_px(im + (long long)c * kp.sC) : 0.0f) : kp.invalid;
+        asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(o + (long long)c * P), "f"(v) : "memory");
+      }
+    }
+    return;
+  }
   // grid_sample, align_corners=False, zero padding
   const float fx = unnormalise(gx, kp.W), fy = unnormalise(gy, kp.H);
   const float x0f = floorf(fx), y0f = floorf(fy);

@@ -59,9 +59,34 @@ class CameraModelRotation:
         """img [N, C, H, W] or [C, H, W] with any strides — e.g. `frames.permute(0, 3, 1, 2)` of the HWC camera buffers,
         no copy — float32, or uint8 which is scaled to [0, 1] on load like preprocess_imgs does
         (api/inference_pytorch.py:55-57), on a CUDA device -> (sampled [N, C, Ht, Wt] float32, valid_mask [Ht, Wt] bool).
-        Only `interpolation='linear'` is implemented (what preprocess_imgs uses); anything else raises."""
-        if interpolation != "linear" or blend_func is not None:
-            raise NotImplementedError("mvs_gi_b200 resampler: only interpolation='linear' is implemented")
+        interpolation: 'linear' (what preprocess_imgs uses), 'nearest', or 'blended' with `blend_func(img) -> factor in
+        [0, 1]` (1 = nearest only), the three modes of the reference sampler (camera_model_sampler.py:98-163)."""
+        if interpolation == "blended":
+            return self.blend_interpolation(img, blend_func, invalid_pixel_value)
+        if interpolation not in ("linear", "nearest"):
+            raise NotImplementedError(f"mvs_gi_b200 resampler: interpolation {interpolation!r} is not one of "
+                                      "'linear', 'nearest', 'blended'")
+        if blend_func is not None:
+            raise ValueError("blend_func is only used by interpolation='blended'")
+        invalid = float(self.default_invalid_value if invalid_pixel_value is None else invalid_pixel_value)
+        return self._sample(self._as_batch(img), interpolation == "nearest", invalid)
+
+    def blend_interpolation(self, img: Tensor, blend_func, invalid_pixel_value=None):
+        """f * nearest + (1 - f) * linear, f = blend_func(img) sampled 'nearest' (camera_model_sampler.py:122-163)."""
+        if blend_func is None:
+            raise ValueError("interpolation='blended' needs blend_func")
+        invalid = float(self.default_invalid_value if invalid_pixel_value is None else invalid_pixel_value)
+        img = self._as_batch(img)
+        if img.dtype == torch.uint8:  # the reference blends the converted float image (convert_input)
+            img = img.float() / 255.0
+        lin, valid = self._sample(img, False, 0.0)
+        near, _ = self._sample(img, True, 0.0)
+        f, _ = self._sample(self._as_batch(blend_func(img).to(torch.float32)), True, 0.0)
+        out = f * near + (1 - f) * lin
+        out[..., ~valid] = invalid
+        return out, valid
+
+    def _as_batch(self, img: Tensor) -> Tensor:
         if not img.is_cuda:
             raise RuntimeError(f"mvs_gi_b200: `img` must be a CUDA tensor (got {img.device}); there is no CPU path")
         if img.dim() == 3:
@@ -70,6 +95,9 @@ class CameraModelRotation:
             raise RuntimeError("img must be [N, C, H, W] or [C, H, W]")
         if img.dtype not in (torch.float32, torch.uint8):
             raise RuntimeError(f"img dtype {img.dtype} not supported (float32, uint8)")
+        return img
+
+    def _sample(self, img: Tensor, nearest: bool, invalid: float):
         N, Cc, H, W = img.shape
         raw = self.camera_model_raw
         if (H, W) != (raw.H, raw.W):  # check_input_shape, camera_model_sampler.py:92-96
@@ -81,12 +109,14 @@ class CameraModelRotation:
         a = abi.MvsgiResampleArgs()
         a.struct_size = C.sizeof(abi.MvsgiResampleArgs)
         a.flags = abi.RESAMPLE_IMG_U8 if img.dtype == torch.uint8 else 0  # v / 255 on load, no float copy of the image
+        if nearest:
+            a.flags |= abi.RESAMPLE_NEAREST
         a.batch, a.channels, a.in_h, a.in_w = N, Cc, H, W
         a.img = img.data_ptr()
         for i, s in enumerate(img.stride()):
             a.img_stride[i] = int(s)
         a.rig = C.pointer(self._struct)
-        a.invalid_value = float(self.default_invalid_value if invalid_pixel_value is None else invalid_pixel_value)
+        a.invalid_value = invalid
         a.out = out.data_ptr()
         a.valid_out = valid.data_ptr()
         with torch.cuda.device(img.device):

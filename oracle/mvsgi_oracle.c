@@ -577,6 +577,40 @@ void orc_resample(const MvsgiRig* rig, const float* img, int N, int C, int H, in
     }
 }
 
+/* CameraModelRotation.__call__(interpolation='nearest') (camera_model_sampler.py:98-120): F.grid_sample(mode='nearest',
+ * zeros padding, align_corners=True — planar_as_base.py:127-133).  ATen: unnormalise ((g + 1) / 2) * (size - 1), round
+ * half to even (nearbyint), a sample outside the image is 0; invalid rays get `invalid`. */
+void orc_resample_nearest(const MvsgiRig* rig, const float* img, int N, int C, int H, int W, float invalid, float* out,
+                          uint8_t* valid_out, const float* grid_in, const uint8_t* valid_in) {
+  const int Ht = rig->cv_height, Wt = rig->cv_width;
+  const MvsgiCamera* c = &rig->cams[0];
+#pragma omp parallel for schedule(static)
+  for (int h = 0; h < Ht; ++h)
+    for (int w = 0; w < Wt; ++w) {
+      float ray[3], gx, gy;
+      int valid;
+      orc_cv_ray(rig, h, w, ray);
+      float x = (c->rot[0] * ray[0] + c->rot[1] * ray[1]) + c->rot[2] * ray[2];
+      float y = (c->rot[3] * ray[0] + c->rot[4] * ray[1]) + c->rot[5] * ray[2];
+      float z = (c->rot[6] * ray[0] + c->rot[7] * ray[1]) + c->rot[8] * ray[2];
+      orc_project(c, x, y, z, &gx, &gy, &valid);
+      if (grid_in) {
+        gx = grid_in[((int64_t)h * Wt + w) * 2];
+        gy = grid_in[((int64_t)h * Wt + w) * 2 + 1];
+        valid = valid_in[(int64_t)h * Wt + w] != 0;
+      }
+      if (valid_out) valid_out[(int64_t)h * Wt + w] = (uint8_t)valid;
+      float fx = nearbyintf(((gx + 1.0f) / 2.0f) * (float)(W - 1)), fy = nearbyintf(((gy + 1.0f) / 2.0f) * (float)(H - 1));
+      int inb = valid && fx >= 0.0f && fx <= (float)(W - 1) && fy >= 0.0f && fy <= (float)(H - 1);
+      long xn = inb ? (long)fx : 0, yn = inb ? (long)fy : 0;
+      for (int n = 0; n < N; ++n)
+        for (int ch = 0; ch < C; ++ch) {
+          const float* im = img + ((int64_t)n * C + ch) * H * W;
+          out[(((int64_t)n * C + ch) * Ht + h) * Wt + w] = valid ? (inb ? im[yn * W + xn] : 0.0f) : invalid;
+        }
+    }
+}
+
 int orc_num_threads(void) {
 #if defined(_OPENMP)
   return omp_get_max_threads();

@@ -186,7 +186,8 @@ def bf16_round(a: np.ndarray) -> np.ndarray:
     return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
 
 
-def resample(rig_struct: abi.MvsgiRig, img, invalid_value: float = 0.0, grid=None, grid_valid=None):
+def resample(rig_struct: abi.MvsgiRig, img, invalid_value: float = 0.0, grid=None, grid_valid=None,
+             interpolation: str = "linear"):
     """CameraModelRotation (camera_model_sampler.py:55-120): img [N,C,H,W] -> (out [N,C,Ht,Wt], valid [Ht,Wt] bool).
     rig_struct as built by mvs_gi_b200.resample.resample_rig.  `grid` [Ht,Wt,2] + `grid_valid` [Ht,Wt]: sample with
     this grid (the CUDA kernel's own, from mvsgi_project_only) instead of the one evaluated here."""
@@ -198,6 +199,17 @@ def resample(rig_struct: abi.MvsgiRig, img, invalid_value: float = 0.0, grid=Non
     if grid is not None:
         grid = _f32(grid).reshape(Ht, Wt, 2)
         grid_valid = np.ascontiguousarray(np.asarray(grid_valid).reshape(Ht, Wt), dtype=np.uint8)
-    lib().orc_resample(C.byref(rig_struct), _p(img), N, Cc, H, W, C.c_float(invalid_value), _p(out), _p(valid),
-                       _p(grid), _p(grid_valid))
+    fn = {"linear": lib().orc_resample, "nearest": lib().orc_resample_nearest}[interpolation]
+    fn(C.byref(rig_struct), _p(img), N, Cc, H, W, C.c_float(invalid_value), _p(out), _p(valid), _p(grid), _p(grid_valid))
     return out, valid.astype(bool)
+
+
+def resample_blended(rig_struct: abi.MvsgiRig, img, blend_factor, invalid_value: float = 0.0, grid=None, grid_valid=None):
+    """CameraModelRotation.blend_interpolation (camera_model_sampler.py:122-163): f * nearest + (1 - f) * linear with the
+    blend factor image f = blend_func(img) itself sampled 'nearest'; invalid rays get `invalid_value`."""
+    lin, valid = resample(rig_struct, img, 0.0, grid, grid_valid, "linear")
+    near, _ = resample(rig_struct, img, 0.0, grid, grid_valid, "nearest")
+    f, _ = resample(rig_struct, blend_factor, 0.0, grid, grid_valid, "nearest")
+    out = (f * near + (np.float32(1) - f) * lin).astype(np.float32)
+    out[:, :, ~valid] = np.float32(invalid_value)
+    return out, valid
