@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MVSGI_ABI_VERSION 10
+#define MVSGI_ABI_VERSION 11
 #define MVSGI_MAX_CAMS 4
 #define MVSGI_MAX_CANDS 64
 #define MVSGI_MAX_PEERS 7 /* extra destinations of a candidate-sharded sweep (8 GPUs of one box) */
@@ -189,6 +189,19 @@ typedef struct MvsgiSweepArgs {
   int32_t num_peers;
   int32_t reserved1;
   float* peer_vols[MVSGI_MAX_PEERS];
+
+  /* Cost-balanced work assignment (optional; static calibration and static masks).  By default every resident CTA
+   * sweeps an equal share of 8-pixel octets dealt round-robin over the image, which balances the CTAs only
+   * statistically: at G16V the per-CTA cost (cameras actually sampled per voxel) spreads +-15 % around its mean.
+   * octet_order is a DEVICE table [order_runs][order_units] of octet indices (pixel >> 3, row-major output pixels),
+   * -1 = empty slot, in which every octet of the image appears exactly once: run r sweeps the octets of row r.
+   * Shape from mvsgi_sweep_balance_shape, costs from mvsgi_sweep_octet_cost; the assignment itself (longest-
+   * processing-time-first) is host code (mvs_gi_b200/ops.py).  The volume is bit-identical with any valid table.
+   * NULL = the default assignment.  Measured (profiles/r3j_balance.jsonl, profiles/r3i_cta_times.txt): the CTAs of
+   * the G16V sweep finish between 332 and 405 us with the round-robin deal and within 345-353 us (one straggler at
+   * 375) with the table; the drop-in modules and bench.py use it by default (balance_runs, --balance). */
+  const int32_t* octet_order;
+  int32_t order_runs, order_units;
 } MvsgiSweepArgs;
 
 /* Scratch the sweep needs for this problem (channels-last staging of feats when
@@ -198,6 +211,19 @@ int64_t mvsgi_sweep_workspace_bytes(const MvsgiSweepArgs* args);
 
 /* Enqueue staging (if needed) + the fused sweep/aggregate kernel. */
 int mvsgi_sweep_f32(const MvsgiSweepArgs* args, void* cuda_stream);
+
+/* Shape of the octet_order table this problem accepts: runs = resident CTAs of the sweep (or fewer for tiny images),
+ * units = octets per run, num_octets = ceil(out_h * out_w / 8).  MVSGI_E_UNSUPPORTED when the problem is not swept as
+ * one item per resident CTA (candidate chunks, several waves, per-frame grids): leave octet_order NULL then.
+ * args->octet_order is ignored; args->vol and args->workspace may be NULL (nothing is written). */
+int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* args, int32_t* runs_out, int32_t* units_out, int32_t* num_octets_out);
+
+/* Relative cost of every octet for frame 0 of this problem, written (not accumulated) to cost_out[num_octets] (DEVICE):
+ * per candidate 4 + 10 * (cameras the octet's warp loads: those that at least one of its 8 voxels samples, a voxel
+ * sampling its valid cameras when more than one is valid; all cameras for the concat builder).  std builder: masks must
+ * be MVSGI_MASK_PACKED (mvsgi_pack_masks).  Two launches (zero fill + cost kernel) on the given stream; args->vol and
+ * args->workspace may be NULL. */
+int mvsgi_sweep_octet_cost(const MvsgiSweepArgs* args, int32_t* cost_out, void* cuda_stream);
 
 /* Number of kernels the last-described problem launches (for gpu_launches
  * accounting in bench.py): staging transposes + mask pack + sweep. */

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_CAMS = 4
 MAX_CANDS = 64
 MAX_PEERS = 7
@@ -27,6 +27,8 @@ FLAG_VOL_CHANNELS_LAST = 8
 FLAG_CTA_TABLE = 16
 FLAG_STAGED_FEATS = 32
 FLAG_VOL_BF16 = 64
+# MVSGI_E_* (negative return codes; positive ones are cudaError_t)
+E_NULL, E_SHAPE, E_STRIDE, E_UNSUPPORTED, E_WORKSPACE, E_VERSION = -1, -2, -3, -4, -5, -6
 RESAMPLE_IMG_U8 = 1
 RESAMPLE_NEAREST = 2
 
@@ -97,6 +99,9 @@ class MvsgiSweepArgs(C.Structure):
         ("num_peers", C.c_int32),
         ("reserved1", C.c_int32),
         ("peer_vols", C.c_void_p * MAX_PEERS),
+        ("octet_order", C.c_void_p),
+        ("order_runs", C.c_int32),
+        ("order_units", C.c_int32),
     ]
 
 
@@ -179,6 +184,9 @@ EXPORTS = {
     "mvsgi_sweep_workspace_bytes": (C.c_int64, [C.POINTER(MvsgiSweepArgs)]),
     "mvsgi_sweep_f32": (C.c_int, [C.POINTER(MvsgiSweepArgs), C.c_void_p]),
     "mvsgi_sweep_launch_count": (C.c_int, [C.POINTER(MvsgiSweepArgs)]),
+    "mvsgi_sweep_balance_shape": (C.c_int, [C.POINTER(MvsgiSweepArgs), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_int32)]),
+    "mvsgi_sweep_octet_cost": (C.c_int, [C.POINTER(MvsgiSweepArgs), C.c_void_p, C.c_void_p]),
     "mvsgi_project_only_f32": (C.c_int, [C.POINTER(MvsgiProjectArgs), C.c_void_p]),
     "mvsgi_resample_f32": (C.c_int, [C.POINTER(MvsgiResampleArgs), C.c_void_p]),
     "mvsgi_mask_pitch_words": (C.c_int32, [C.c_int32]),

@@ -37,6 +37,53 @@ __global__ void project_only_kernel(const __grid_constant__ MvsgiRig rig, float*
     }
 }
 
+// ---- octet costs (mvsgi_sweep_octet_cost): what a warp of sweep_kernel will do for an octet.  A warp owns the 8 voxels
+// (octet, candidate) and loads a camera's taps when ANY of the 8 samples it (sweep.cuh: __any_sync(ld)), so the unit of
+// cost is (octet, candidate, camera loaded): measured per-CTA times follow the count of those (R^2 0.69) far better
+// than the count of sampled voxels (0.47), profiles/r3i_cta_times.txt.  Validity as the build step + lookup_masks
+// compute it.  grid (ceil(P / 128), D); 8 consecutive lanes = one octet -> one atomic per octet and warp.
+template <int CAM, int AGG>
+__global__ void __launch_bounds__(128) octet_cost_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig,
+                                                         int* __restrict__ cost) {
+  const int pixr = blockIdx.x * 128 + threadIdx.x, d = blockIdx.y;
+  const bool act = pixr < kp.P;
+  const int pix = act ? pixr : kp.P - 1;
+  const int h = pix / kp.Wo, w = pix - h * kp.Wo;
+  float rx = 0.f, ry = 0.f, rz = 0.f;
+  if (kp.gridMode == MVSGI_GRID_PROJECT) cv_ray(rig, h, w, rx, ry, rz);
+  uint32_t v = 0;  // bit cam: this voxel would sample camera cam
+#pragma unroll
+  for (int cam = 0; cam < CAM; ++cam) {
+    float gx, gy;
+    bool gvalid = true;
+    if (kp.gridMode == MVSGI_GRID_PROJECT) {
+      float x, y, z;
+      to_camera(rig.cams[cam], rx, ry, rz, rig.dist[d], x, y, z);
+      gvalid = project(rig.cams[cam], x, y, z, gx, gy);
+    } else {
+      const float2 g = __ldg(reinterpret_cast<const float2*>(kp.grids + cam * kp.gsCam + d * kp.gsD + h * kp.gsY +
+                                                               w * kp.gsX));
+      gx = g.x;
+      gy = g.y;
+      if (AGG == MVSGI_AGG_STD) gvalid = __ldg(kp.gmask + cam * kp.gmCam + d * kp.gmD + h * kp.gmY + w * kp.gmX) != 0;
+    }
+    if (AGG == MVSGI_AGG_STD) {
+      const uint32_t info = gvalid ? make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch) : kMaskNone;
+      v |= mask_eval(mask_fetch(kp.mbits + cam * kp.mbCam, info, kp.mPitch), info) << cam;  // spherical_sweep_avg.py:92-102
+    } else {
+      v |= 1u << cam;
+    }
+  }
+  if (!act || (AGG == MVSGI_AGG_STD && __popc(v) < 2)) v = 0;  // :106-111: one valid camera samples nothing
+  int loaded = 0;  // cameras whose taps the octet's warp loads for this candidate
+#pragma unroll
+  for (int cam = 0; cam < CAM; ++cam) {
+    const uint32_t any = __ballot_sync(0xFFFFFFFFu, (v >> cam) & 1u);
+    loaded += ((any >> (threadIdx.x & 24)) & 0xFFu) != 0u;
+  }
+  if ((threadIdx.x & 7) == 0 && act) atomicAdd(cost + (pixr >> 3), 4 + 10 * loaded);
+}
+
 }  // namespace mvsgi
 
 namespace {
@@ -66,6 +113,9 @@ struct SweepPlan {
   int64_t feats_bytes, mask_bytes, flag_bytes, total_bytes;
   int dch, num_chunks, num_runs, run_len, num_items, max_pairs, grid, group_px, interleave, unit_oct;
   int cta_fb;             // frames per pass of sweep_kernel (sweep.cuh, sweep_frames_per_pass)
+  bool oct_order;         // runs follow MvsgiSweepArgs.octet_order
+  int grid_target;        // resident CTAs of the sweep kernel
+  bool one_item_per_cta;  // the default plan is one (run, all candidates) item per resident CTA, single octets
   size_t smem_bytes;
   int cout;
   bool walk;              // channels-last volume: sweep_walk.cuh (experiment builds only)
@@ -264,6 +314,22 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   // C=48 -11 %, DoubleSphere -16 %, high-D +1 %)
   p->group_px = env_int("MVSGI_GROUP_PX", p->interleave ? p->run_len : 32);
   if (p->group_px < 1) p->group_px = 1;
+  p->grid_target = grid_target;
+  p->one_item_per_cta = p->num_chunks == 1 && unit == 1 && p->num_items <= grid_target && !p->per_frame_grids && !p->tiled;
+  p->oct_order = false;
+  if (a->octet_order != nullptr) {  // cost-balanced runs: same table budget, the caller's assignment of octets to runs
+    const int64_t cap = budget / (8 * per_px);
+    if (!p->one_item_per_cta || a->order_runs < 1 || a->order_runs > grid_target || a->order_units < 1 ||
+        a->order_units > cap || (int64_t)a->order_runs * a->order_units < num_oct)
+      return MVSGI_E_UNSUPPORTED;
+    p->oct_order = true;
+    p->num_runs = a->order_runs;
+    p->run_len = 8 * a->order_units;
+    p->num_items = p->num_runs;
+    p->max_pairs = p->run_len * dch;
+    p->grid = p->num_items;
+    p->group_px = p->run_len;
+  }
   p->smem_bytes = align_up((int64_t)p->max_pairs * per_pair + (int64_t)p->run_len * 12 + 16, 16);
   p->walk = false;
 
@@ -343,6 +409,8 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   kp.P = a->out_h * a->out_w; kp.numRuns = p.num_runs; kp.runLen = p.run_len; kp.dch = p.dch;
   kp.numChunks = p.num_chunks; kp.numItems = p.num_items; kp.maxPairs = p.max_pairs; kp.grpPx = p.group_px; kp.interleave = p.interleave; kp.unitOct = p.unit_oct;
   kp.framesPerPass = p.cta_fb;
+  kp.octOrder = p.oct_order ? a->octet_order : nullptr;
+  kp.octUnits = p.oct_order ? a->order_units : 0;
   kp.wL = p.walk ? p.w_len : 0; kp.wSegs = p.walk ? p.w_segs : 0; kp.wNumSeg = p.walk ? p.w_num_seg : 0;
   if (p.direct) {  // the caller's channels-last tensor: element (b, cam, y, x, c) at b*s0 + cam*s1 + y*s3 + x*s4 + c
     kp.feat = a->feats;
@@ -523,6 +591,61 @@ int64_t mvsgi_sweep_workspace_bytes(const MvsgiSweepArgs* a) {
   SweepPlan p;
   const int rc = validate_and_plan(a, &p);
   return rc != MVSGI_OK ? (int64_t)rc : p.total_bytes;
+}
+
+int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* a, int32_t* runs_out, int32_t* units_out, int32_t* num_octets_out) {
+  if (a == nullptr || runs_out == nullptr || units_out == nullptr || num_octets_out == nullptr) return MVSGI_E_NULL;
+  MvsgiSweepArgs b = *a;
+  b.octet_order = nullptr;
+  b.order_runs = b.order_units = 0;
+  if (b.vol == nullptr) b.vol = reinterpret_cast<float*>(static_cast<uintptr_t>(256));  // never written here: the problem may be described without outputs
+  SweepPlan p;
+  const int rc = validate_and_plan(&b, &p);
+  if (rc != MVSGI_OK) return rc;
+  if (!p.one_item_per_cta) return MVSGI_E_UNSUPPORTED;
+  const int num_oct = (a->out_h * a->out_w + 7) / 8;
+  const int runs = num_oct < p.grid_target ? num_oct : p.grid_target;
+  *runs_out = runs;
+  *units_out = (num_oct + runs - 1) / runs;  // <= the default plan's octets per run, so the table fits
+  *num_octets_out = num_oct;
+  return MVSGI_OK;
+}
+
+int mvsgi_sweep_octet_cost(const MvsgiSweepArgs* a, int32_t* cost_out, void* stream) {
+  if (a == nullptr || cost_out == nullptr) return MVSGI_E_NULL;
+  MvsgiSweepArgs b = *a;
+  b.octet_order = nullptr;
+  b.order_runs = b.order_units = 0;
+  if (b.vol == nullptr) b.vol = reinterpret_cast<float*>(static_cast<uintptr_t>(256));  // never written here: the problem may be described without outputs
+  SweepPlan p;
+  const int rc = validate_and_plan(&b, &p);
+  if (rc != MVSGI_OK) return rc;
+  const bool std_agg = a->aggregate == MVSGI_AGG_STD;
+  if (p.per_frame_grids || (std_agg && p.pack_masks)) return MVSGI_E_UNSUPPORTED;  // packed masks only
+  mvsgi::SweepKP kp;
+  fill_kp(&b, p, nullptr, nullptr, kp);
+  MvsgiRig rig;
+  if (a->grid_mode == MVSGI_GRID_PROJECT) rig = *a->rig;
+  else memset(&rig, 0, sizeof(rig));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int num_oct = (kp.P + 7) / 8;
+  cudaError_t e = cudaMemsetAsync(cost_out, 0, (size_t)num_oct * sizeof(int32_t), st);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((kp.P + 127) / 128, a->num_cands);
+  if (grid.y > 65535) return MVSGI_E_SHAPE;
+#define MVSGI_COST(CAM)                                                                                      \
+  if (std_agg) mvsgi::octet_cost_kernel<CAM, MVSGI_AGG_STD><<<grid, 128, 0, st>>>(kp, rig, cost_out);         \
+  else mvsgi::octet_cost_kernel<CAM, MVSGI_AGG_CONCAT><<<grid, 128, 0, st>>>(kp, rig, cost_out)
+  switch (a->num_cams) {
+    case 1: MVSGI_COST(1); break;
+    case 2: MVSGI_COST(2); break;
+    case 3: MVSGI_COST(3); break;
+    case 4: MVSGI_COST(4); break;
+    default: return MVSGI_E_UNSUPPORTED;
+  }
+#undef MVSGI_COST
+  g_launches++;
+  return (int)cudaGetLastError();
 }
 
 int mvsgi_sweep_launch_count(const MvsgiSweepArgs* a) {

@@ -61,6 +61,10 @@ struct SweepKP {
   int P, numRuns, runLen, dch, numChunks, numItems, maxPairs, grpPx, interleave;
   int framesPerPass;  // the FB instantiation of sweep_kernel: 1, or sweep_frames_per_pass() (static masks, shared grids)
   int unitOct;  // interleaved runs are dealt in units of unitOct vertically stacked octets (1 = single octets)
+  // cost-balanced runs (MvsgiSweepArgs.octet_order): run r owns octets octOrder[r * octUnits + k], k < octUnits
+  // (-1 = empty slot); nullptr = the interleaved / contiguous assignment below
+  const int* octOrder;
+  int octUnits;
   int wL, wSegs, wNumSeg;  // sweep_walk.cuh: segment length, segments per run, segments in the image
   // staged features: element (b, cam, cg, yp, xp, c) at feat[b*fsB + cam*fsCam + cg*fsCg + yp*fsY + xp*16 + c]
   const float* feat;
@@ -261,11 +265,28 @@ template <> struct VolT<true> { typedef uint16_t type; };
 // The record stride is odd, so the 8 records a warp reads at a time sit in 8 different banks.
 __host__ __device__ constexpr int entry_words(int cam) { return (2 + 3 * cam) | 1; }
 
+#ifdef MVSGI_CTA_TIMES  // diagnostic builds: (smid, start, end of the build, end) of every CTA, globaltimer ns
+__device__ unsigned long long g_cta_times[4 * 1024];
+MVSGI_DEV unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
 template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16, bool DIRECT = false, bool VBF16 = false,
           int FB = 1>
 __global__ void __launch_bounds__(sweep_threads(FB), sweep_ctas(FB))
 sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   constexpr int NT = sweep_threads(FB);
+#ifdef MVSGI_CTA_TIMES
+  if (threadIdx.x == 0 && blockIdx.x < 1024) {
+    unsigned sm;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    g_cta_times[4 * blockIdx.x] = sm;
+    g_cta_times[4 * blockIdx.x + 1] = gtimer();
+  }
+#endif
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int ES = entry_words(CAM);
   const int MP = kp.maxPairs;
@@ -288,7 +309,10 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
     int p0, npx;
     const int U = kp.unitOct, octPerRow = kp.Wo >> 3;  // U > 1: host guarantees Wo % 8 == 0 and Ho % U == 0
     const int numUnits = U > 1 ? (kp.Ho / U) * octPerRow : numOct;
-    if (kp.interleave) {
+    if (kp.octOrder != nullptr) {
+      p0 = 0;
+      npx = 8 * kp.octUnits;
+    } else if (kp.interleave) {
       p0 = 0;
       npx = 8 * U * ((numUnits - run + kp.numRuns - 1) / kp.numRuns);
     } else {
@@ -298,6 +322,10 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
     // U stacked octets share feature rows between them (vertical neighbours sample rows 1.6 apart), and a run's units
     // are still spread over the image for load balance
     auto pixel_of = [&](int p) {
+      if (kp.octOrder != nullptr) {  // an empty slot maps past the image: its records are inactive
+        const int o = __ldg(kp.octOrder + run * kp.octUnits + (p >> 3));
+        return o >= 0 ? 8 * o + (p & 7) : kp.P + (p & 7);
+      }
       if (!kp.interleave) return p0 + p;
       const int k = p >> 3;
       if (U == 1) return 8 * (run + kp.numRuns * k) + (p & 7);
@@ -395,6 +423,9 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       }
     }
 
+#ifdef MVSGI_CTA_TIMES
+    if (threadIdx.x == 0 && blockIdx.x < 1024) g_cta_times[4 * blockIdx.x + 2] = gtimer();
+#endif
     // ---------------------------------------------------------------- sweep: frames outer, FB frames per pass
     // (FB > 1: host guarantees static masks and shared grids, so the table is the same for every frame)
     for (int b0 = 0; b0 < kp.B; b0 += FB) {
@@ -565,6 +596,9 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
     }
     // (the barrier above also protects the table: the next item's build overwrites it)
   }
+#ifdef MVSGI_CTA_TIMES
+  if (threadIdx.x == 0 && blockIdx.x < 1024) g_cta_times[4 * blockIdx.x + 3] = gtimer();
+#endif
 }
 
 }  // namespace mvsgi

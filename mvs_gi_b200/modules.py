@@ -75,6 +75,14 @@ class _SweepBase(nn.Module):
         # True: every new masks tensor is checked for negative / NaN values when it is packed (one device->host sync per
         # new tensor; off by default so that a forward stays CUDA-graph capturable); set_static_masks always checks.
         self.check_masks = False
+        # Cost-balanced work assignment (ops.balanced_octet_order): with an attached rig and static masks the per-octet
+        # cost of the sweep is known in advance; the octets are dealt to the resident CTAs so that every CTA samples
+        # about the same number of cameras.  Same volume bit for bit; computed once per shape (one synchronisation).
+        # Measured on B200 (profiles/r3j_balance.jsonl): the per-CTA times of the round-robin deal spread from 332 to
+        # 405 us at G16V and follow the count of (octet, candidate, camera loaded by the warp); dealt by that count they
+        # lie within 345-353 us and the kernel ends 7 % earlier.  Set to False to keep the round-robin deal.
+        self.balance_runs = True
+        self._order_cache = None  # (key, int32 [runs, units] table or None)
         # Memory layout of the volume the sweep kernel writes.  False = the reference's NCDHW.  True = the same
         # [B,C,D,Ho,Wo] tensor with torch.channels_last_3d strides: the kernel then stores 512 contiguous bytes per
         # warp and post_vol's Conv3d runs cuDNN's NDHWC path on it.  Values are identical.
@@ -89,6 +97,7 @@ class _SweepBase(nn.Module):
         """Evaluate the sampling grid in-kernel from this calibration instead of reading `grids`."""
         self._rig = rig
         self._rig_blob = ops.rig_to_blob(rig.to_struct()) if rig is not None else None
+        self._order_cache = None
         return self
 
     def set_vol_channels_last(self, on: bool = True) -> "_SweepBase":
@@ -121,6 +130,7 @@ class _SweepBase(nn.Module):
         """Inference: masks are the same for every frame ([1|B, CAM, 1, Hm, Wm]); only frame 0 is kept and shared."""
         self._static_masks = None if masks is None else masks[:1].contiguous()
         self._mask_cache = None
+        self._order_cache = None
         if self._static_masks is not None and self._static_masks.is_cuda:
             self._packed_masks(self._static_masks, check=True)
         return self
@@ -171,9 +181,31 @@ class _SweepBase(nn.Module):
                 raise RuntimeError("the std builder needs masks")
             if masks.is_cuda and masks.dim() == 5 and masks.dtype in (torch.float32, torch.bool, torch.uint8):
                 masks, (mask_h, mask_w) = self._packed_masks(masks, check=self.check_masks)
+        order = None
+        if (self.balance_runs and self._rig_blob is not None and not want_valid and feats.is_cuda and
+                (masks is None or (self._static_masks is not None and masks.dtype == torch.int32))):
+            order = self._octet_order(feats, masks, mask_h, mask_w, int(Ho), int(Wo), int(D))
         return ops.sweep_op(feats, grids, grid_masks, masks, self._rig_blob, self._aggregate, int(Ho), int(Wo), int(D),
                             want_valid, self.vol_channels_last, self.feats_bf16, mask_h, mask_w,
-                            self.vol_bf16 and not want_valid)
+                            self.vol_bf16 and not want_valid, order)
+
+    def _octet_order(self, feats: Tensor, bits: Optional[Tensor], mask_h: int, mask_w: int, Ho: int, Wo: int, D: int):
+        """Cost-balanced assignment of the output image's octets to the sweep's CTAs (ops.balanced_octet_order) for
+        the attached rig and the static masks: computed at the first call with a given shape (one device
+        synchronisation, skipped while a CUDA graph is being captured) and kept, like the packed masks."""
+        key = (tuple(feats.shape), tuple(feats.stride()), None if bits is None else (bits.data_ptr(), bits._version),
+               mask_h, mask_w, Ho, Wo, D, self.vol_channels_last, self.feats_bf16, self.vol_bf16, feats.device)
+        c = self._order_cache
+        if c is not None and c[0] == key:
+            return c[1]
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        call = ops.SweepCall(feats, None, None, bits, self._rig_blob, self._aggregate, Ho, Wo, D, describe_only=True,
+                             channels_last=self.vol_channels_last, feats_bf16=self.feats_bf16,
+                             mask_hw=(mask_h, mask_w) if mask_h > 0 else None, vol_bf16=self.vol_bf16)
+        order = ops.balanced_octet_order(call)
+        self._order_cache = (key, order)
+        return order
 
 
 class SphericalSweepStdMasked(_SweepBase):

@@ -54,7 +54,8 @@ class SweepCall:
                  want_valid: bool = False, out: Optional[Tensor] = None, cand_offset: int = 0,
                  peer_ptrs: Sequence[int] = (), describe_only: bool = False, channels_last: bool = False,
                  feats_bf16: bool = False, cta_table: bool = False, staged_feats: bool = False,
-                 mask_hw: Optional[Tuple[int, int]] = None, vol_bf16: bool = False):
+                 mask_hw: Optional[Tuple[int, int]] = None, vol_bf16: bool = False,
+                 octet_order: Optional[Tensor] = None):
         """`out`, `cand_offset`, `peer_ptrs`: candidate-sharded sweep.  `out` is the full [B, Cout, Dvol, Ho, Wo]
         volume (contiguous); this call fills candidates [cand_offset, cand_offset + num_cands) of it and of every
         peer-mapped volume in `peer_ptrs` (raw device pointers from sharding.PeerVolume).
@@ -69,6 +70,8 @@ class SweepCall:
         (MVSGI_FLAG_STAGED_FEATS; same volume, for tests and bench.py).
         `vol_bf16`: the volume is written as bfloat16 (MVSGI_FLAG_VOL_BF16, needs `channels_last`; stated-tolerance
         mode for a bf16 post_vol on the tensor cores).
+        `octet_order`: the int32 [runs, units] table of `balanced_octet_order()` (cost-balanced assignment of the
+        image's 8-pixel octets to the resident CTAs; same volume bit for bit).
         `describe_only`: fill the argument struct (inputs only) without allocating the volume or the workspace —
         how the backward op describes the forward problem to mvsgi_sweep_backward_f32."""
         self.lib = abi.load_library()
@@ -201,6 +204,20 @@ class SweepCall:
         a.workspace = self.workspace.data_ptr()
         a.workspace_bytes = self.workspace.numel()
         self.args = a
+        if octet_order is not None:
+            self.set_octet_order(octet_order)
+
+    def set_octet_order(self, order: Optional[Tensor]) -> None:
+        """Attach (or, with None, detach) the table of `balanced_octet_order()`."""
+        a = self.args
+        if order is None:
+            a.octet_order, a.order_runs, a.order_units = None, 0, 0
+            return
+        _require_cuda(order, "octet_order")
+        if order.dtype != torch.int32 or order.dim() != 2 or not order.is_contiguous():
+            raise RuntimeError("octet_order must be a contiguous int32 [runs, units] tensor")
+        a.octet_order, a.order_runs, a.order_units = order.data_ptr(), order.shape[0], order.shape[1]
+        self.keep.append(order)
 
     def launch_count(self, flags: int = 0) -> int:
         self.args.flags = flags | self.base_flags
@@ -216,11 +233,59 @@ class SweepCall:
         abi.check(rc, "mvsgi_sweep_f32")
 
 
+def lpt_assign(cost, runs: int, units: int):
+    """Deal octets (index = position in `cost`) to `runs` runs of at most `units` slots so that the runs' total costs
+    are as equal as their equal cardinality allows: longest-processing-time-first in rounds — the octets in descending
+    cost, `runs` at a time, the dearest of a round to the run that is lightest so far — so every run gets one octet per
+    round and the spread left after a round is at most the spread of costs inside it.
+    -> int32 [runs, units], -1 = empty slot; every octet appears exactly once."""
+    import numpy as np
+
+    cost = np.asarray(cost, dtype=np.int64)
+    n = int(cost.size)
+    if runs * units < n:
+        raise ValueError("more octets than slots")
+    order = np.full((runs, units), -1, dtype=np.int32)
+    load = np.zeros(runs, dtype=np.int64)
+    desc = np.argsort(-cost, kind="stable")
+    for k in range(units):
+        chunk = desc[k * runs:(k + 1) * runs]
+        if chunk.size == 0:
+            break
+        light = np.argsort(load, kind="stable")[:chunk.size]  # lightest runs first
+        order[light, k] = chunk
+        load[light] += cost[chunk]
+    # compact: empty slots (only possible in the last, partial round) stay at the end of their run by construction
+    return order
+
+
+def balanced_octet_order(call: "SweepCall") -> Optional[Tensor]:
+    """Cost-balanced assignment of the image's octets to the sweep's resident CTAs for the problem `call` describes
+    (static calibration, packed static masks): the per-octet cost comes from the device (mvsgi_sweep_octet_cost, the
+    cameras each voxel will sample), the assignment is longest-processing-time-first on the host.  One device
+    synchronisation — meant to be done once per (rig, masks, shape) and cached, like the packed masks.  None when the
+    problem is not swept as one item per resident CTA (high-D, per-frame grids): the default assignment stays."""
+    lib = call.lib
+    runs, units, noct = C.c_int32(), C.c_int32(), C.c_int32()
+    rc = lib.mvsgi_sweep_balance_shape(C.byref(call.args), C.byref(runs), C.byref(units), C.byref(noct))
+    if rc == abi.E_UNSUPPORTED:
+        return None
+    abi.check(rc, "mvsgi_sweep_balance_shape")
+    cost = torch.empty((noct.value,), dtype=torch.int32, device=call.device)
+    with torch.cuda.device(call.device):
+        rc = lib.mvsgi_sweep_octet_cost(C.byref(call.args), cost.data_ptr(), _stream_ptr(call.device))
+    if rc == abi.E_UNSUPPORTED:
+        return None
+    abi.check(rc, "mvsgi_sweep_octet_cost")
+    order = lpt_assign(cost.cpu().numpy(), runs.value, units.value)
+    return torch.from_numpy(order).to(call.device)
+
+
 def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                channels_last=False, feats_bf16=False, mask_h=0, mask_w=0, vol_bf16=False):
+                channels_last=False, feats_bf16=False, mask_h=0, mask_w=0, vol_bf16=False, octet_order=None):
     call = SweepCall(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
                      channels_last=channels_last, feats_bf16=feats_bf16,
-                     mask_hw=(mask_h, mask_w) if mask_h > 0 else None, vol_bf16=vol_bf16)
+                     mask_hw=(mask_h, mask_w) if mask_h > 0 else None, vol_bf16=vol_bf16, octet_order=octet_order)
     call.run()
     # inputs and workspace are only read by kernels already enqueued on this stream; the caching allocator reuses
     # freed blocks in stream order, so dropping the references here is safe.
@@ -231,16 +296,16 @@ def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out
 def sweep_op(feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor], masks: Optional[Tensor],
              rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
              want_valid: bool, channels_last: bool = False, feats_bf16: bool = False, mask_h: int = 0,
-             mask_w: int = 0, vol_bf16: bool = False) -> Tuple[Tensor, Tensor]:
+             mask_w: int = 0, vol_bf16: bool = False, octet_order: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """`masks`: [B|1, CAM, 1, Hm, Wm] float32 / bool / uint8 (reference interface), or the int32 bits of pack_masks()
-    with mask_h, mask_w = the size of the masks they were packed from."""
+    with mask_h, mask_w = the size of the masks they were packed from.  `octet_order`: balanced_octet_order()."""
     return _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                       channels_last, feats_bf16, mask_h, mask_w, vol_bf16)
+                       channels_last, feats_bf16, mask_h, mask_w, vol_bf16, octet_order)
 
 
 @sweep_op.register_fake
 def _(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid, channels_last=False,
-      feats_bf16=False, mask_h=0, mask_w=0, vol_bf16=False):
+      feats_bf16=False, mask_h=0, mask_w=0, vol_bf16=False, octet_order=None):
     B, CAM, Cc = feats.shape[:3]
     cout = Cc if aggregate == abi.AGG_STD else CAM * Cc
     vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=torch.bfloat16 if vol_bf16 else feats.dtype,
@@ -339,7 +404,7 @@ def _sweep_bwd(ctx, grad_vol, grad_valid):
     if ctx.needs_input_grad[0] and grad_vol is not None:
         grad_vol = grad_vol.float()  # a bfloat16 volume (vol_bf16) hands back a bfloat16 gradient
         gf = sweep_backward_op(grad_vol, feats, grids, grid_masks, masks, rig_blob, *ctx.meta)
-    return gf, None, None, None, None, None, None, None, None, None, None, None, None, None, None
+    return gf, None, None, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 sweep_op.register_autograd(_sweep_bwd, setup_context=_sweep_setup)

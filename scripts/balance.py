@@ -38,3 +38,34 @@ rowcost = per_px.reshape(Ho, Wo).sum(1)
 print("row cost (first 10, mid, last):", rowcost[:5], rowcost[38:42], rowcost[-5:])
 colcost = per_px.reshape(Ho, Wo).sum(0)
 print("col cost by 32-px block:", colcost.reshape(10, 32).sum(1))
+
+# ---- the shipped assignment: octet-interleaved runs (run r owns octets r, r + runs, r + 2 runs, ...)
+octs = (P + 7) // 8
+oct_cost = per_px[: octs * 8].reshape(octs, 8).sum(1) + 0.3 * 16 * 8
+for nruns in (291, 296):
+    cost = np.array([oct_cost[r::nruns].sum() for r in range(nruns)])
+    print(f"interleaved runs {nruns}: max/mean = {cost.max()/cost.mean():.3f}, min/mean = {cost.min()/cost.mean():.3f}, "
+          f"std/mean = {cost.std()/cost.mean():.3f}")
+    sm = cost[:148].copy()
+    sm[: nruns - 148] += cost[148:]
+    print(f"   per SM (CTA i and i + 148 together): max/mean = {sm.max()/sm.mean():.3f}, min/mean = {sm.min()/sm.mean():.3f}")
+# greedy: octets sorted by cost, each to the currently lightest run with room (<= 11 octets)
+order = np.argsort(-oct_cost)
+nruns = 296
+load = np.zeros(nruns); cnt = np.zeros(nruns, int)
+import heapq
+h = [(0.0, r) for r in range(nruns)]
+heapq.heapify(h)
+cap = (octs + nruns - 1) // nruns
+for o in order:
+    while True:
+        l, r = heapq.heappop(h)
+        if cnt[r] < cap:
+            break
+    load[r] += oct_cost[o]; cnt[r] += 1
+    heapq.heappush(h, (load[r], r))
+print(f"greedy LPT over {nruns} runs (<= {cap} octets each): max/mean = {load.max()/load.mean():.3f}, min/mean = {load.min()/load.mean():.3f}")
+from mvs_gi_b200 import ops as _ops
+_ord = _ops.lpt_assign((oct_cost * 10).astype(np.int64), 296, 11)
+_load = np.array([oct_cost[o[o >= 0]].sum() for o in _ord])
+print(f"round-wise LPT (ops.lpt_assign) over 296 runs: max/mean = {_load.max()/_load.mean():.3f}, min/mean = {_load.min()/_load.mean():.3f}")

@@ -8,6 +8,8 @@ FL="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler 
 nvcc $FL -c -o $OBJ/mvsgi_b200.o mvsgi_b200.cu &
 nvcc $FL -c -o $OBJ/sweep_cta.o sweep_cta.cu &
 nvcc $FL -Xptxas -v -c -o $OBJ/sweep_cta_fb.o sweep_cta_fb.cu > $OBJ/ptxas.log 2>&1 &
+nvcc $FL -c -o $OBJ/softargmin_tma.o softargmin_tma.cu &
+nvcc $FL -c -o $OBJ/softargmin_bwd.o softargmin_bwd.cu &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libmvsgi_b200_$NAME.so $OBJ/mvsgi_b200.o $OBJ/sweep_cta.o $OBJ/sweep_cta_fb.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libmvsgi_b200_$NAME.so $OBJ/mvsgi_b200.o $OBJ/sweep_cta.o $OBJ/sweep_cta_fb.o $OBJ/softargmin_tma.o $OBJ/softargmin_bwd.o
 grep -A2 "sweep_kernelILi3ELi0ELb1ELb0ELb0ELb1ELb0ELb1ELb0ELi[0-9]E" $OBJ/ptxas.log | grep "registers" | tr '\n' ' '; echo " <- $NAME"

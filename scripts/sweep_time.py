@@ -28,6 +28,13 @@ if os.environ.get("SAMEFRAME"):  # every frame of the batch is the same frame (s
 agg = abi.AGG_STD if w.aggregate == "std" else abi.AGG_CONCAT
 calls = [ops.SweepCall(f, None, None, masks if agg == abi.AGG_STD else None, rig_blob, agg, Ho, Wo, len(w.dist_list),
                        channels_last=True, mask_hw=w.mask_hw) for f in sets]
+balanced = False
+if os.environ.get("BALANCE", "1") != "0":  # cost-balanced runs (ops.balanced_octet_order), computed once
+    order = ops.balanced_octet_order(calls[0])
+    if order is not None:
+        balanced = True
+        for c in calls:
+            c.set_octet_order(order)
 n = len(calls)
 for i in range(2 * n):
     calls[i % n].run()
@@ -45,5 +52,5 @@ vol = calls[0].vol
 chk = int(vol.contiguous().view(torch.int32).to(torch.int64).sum().item())
 cout = vol.shape[1]
 alg = B * (cout * len(w.dist_list) * Ho * Wo * 4 + w.num_cams * Hf * Wf * w.feat_chs * 4)
-print(json.dumps({"lib": os.path.basename(os.environ.get("MVSGI_B200_LIB", "default")), "workload": name, "batch": B,
+print(json.dumps({"lib": os.path.basename(os.environ.get("MVSGI_B200_LIB", "default")), "workload": name, "batch": B, "balanced": balanced,
                   "sweep_ms": round(ms, 4), "frac": round(alg / (ms * 1e-3) / 6537.6e9, 4), "checksum": chk}), flush=True)
