@@ -247,8 +247,9 @@ def workload_config(args, w):
         "masks": args.masks, "feats_layout": args.feats_layout, "vol_layout": args.vol_layout, "norm_costs": bool(args.norm_costs),
         "parallelism": f"frame-sharded x{args.gpus}, no collective",
         "cache": "3 rotating input sets, each > 126 MB L2",
-        "runs": ("output octets dealt to the sweep's CTAs by precomputed cost (static rig + masks, computed once outside "
-                 "the timed region)") if (args.balance == "on" and args.masks != "per_frame") else "round-robin octets",
+        "runs": ("output octets dealt to the sweep's CTAs by precomputed cost, corrected once by measured per-CTA times "
+                 "(static rig + masks; computed outside the timed region, see run_balance)")
+                if (args.balance == "on" and args.masks != "per_frame") else "round-robin octets",
     }
 
 
@@ -299,9 +300,9 @@ def run_b200(args, w):
                            channels_last=args.vol_layout == "ndhwc", mask_hw=mask_hw) for f in feat_sets]
     # static calibration + static masks: the octets of the output image are dealt to the sweep's CTAs by their known
     # cost (ops.balanced_octet_order) — computed once here, outside every timed region, like the packed masks
-    octet_order = None
+    octet_order, balance_report = None, None
     if args.balance == "on" and (not std or args.masks != "per_frame"):
-        octet_order = ops.balanced_octet_order(calls[0])
+        octet_order, balance_report = ops.calibrated_octet_order(calls[0])
         for c in calls:
             c.set_octet_order(octet_order)
     costs_sets = [torch.randn((B, 1, w.num_cands, *w.cv_hw), device=dev, generator=gen) for _ in range(nsets)]
@@ -363,7 +364,7 @@ def run_b200(args, w):
         if balanced is None:
             balanced = octet_order is not None
         if balanced and (not std or mask_mode != "per_frame"):
-            oc.set_octet_order(ops.balanced_octet_order(oc))
+            oc.set_octet_order(ops.calibrated_octet_order(oc)[0])
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(6)]
         for e in ev:
             calls[1].run(abi.FLAG_SWEEP_ONLY if not stage_launches else abi.FLAG_STAGE_ONLY)
@@ -578,7 +579,7 @@ def run_b200(args, w):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, w),
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "run_balance": balance_report,
         "latency_single_frame": latency, "step_algorithmic_gbs": step_gbs, "step_frac_of_peak": step_gbs / peak,
         "cpu_baseline": cpu, "reference_on_gpu": ref_gpu, "dshard": dshard,
     }

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MVSGI_ABI_VERSION 11
+#define MVSGI_ABI_VERSION 12
 #define MVSGI_MAX_CAMS 4
 #define MVSGI_MAX_CANDS 64
 #define MVSGI_MAX_PEERS 7 /* extra destinations of a candidate-sharded sweep (8 GPUs of one box) */
@@ -202,6 +202,12 @@ typedef struct MvsgiSweepArgs {
    * 375) with the table; the drop-in modules and bench.py use it by default (balance_runs, --balance). */
   const int32_t* octet_order;
   int32_t order_runs, order_units;
+
+  /* Optional DEVICE buffer of mvsgi_sweep_grid(args) x 4 uint64: per CTA of the sweep kernel its SM id, start time, end of
+   * its first table build and end time (globaltimer ns).  With octet_order, CTA i sweeps run i, so the times show which
+   * runs — and which SMs: the CTA-to-SM placement of a full one-wave grid repeats from launch to launch — finish late;
+   * ops.calibrated_octet_order() re-deals the octets with them.  NULL = not recorded (no cost). */
+  uint64_t* cta_times_out;
 } MvsgiSweepArgs;
 
 /* Scratch the sweep needs for this problem (channels-last staging of feats when
@@ -217,6 +223,9 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* args, void* cuda_stream);
  * one item per resident CTA (candidate chunks, several waves, per-frame grids): leave octet_order NULL then.
  * args->octet_order is ignored; args->vol and args->workspace may be NULL (nothing is written). */
 int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* args, int32_t* runs_out, int32_t* units_out, int32_t* num_octets_out);
+
+/* CTAs the sweep kernel of this problem is launched with (rows of cta_times_out); negative = error. */
+int mvsgi_sweep_grid(const MvsgiSweepArgs* args);
 
 /* Relative cost of every octet for frame 0 of this problem, written (not accumulated) to cost_out[num_octets] (DEVICE):
  * per candidate 4 + 10 * (cameras the octet's warp loads: those that at least one of its 8 voxels samples, a voxel

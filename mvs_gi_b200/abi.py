@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 MAX_CAMS = 4
 MAX_CANDS = 64
 MAX_PEERS = 7
@@ -102,6 +102,7 @@ class MvsgiSweepArgs(C.Structure):
         ("octet_order", C.c_void_p),
         ("order_runs", C.c_int32),
         ("order_units", C.c_int32),
+        ("cta_times_out", C.c_void_p),
     ]
 
 
@@ -187,6 +188,7 @@ EXPORTS = {
     "mvsgi_sweep_balance_shape": (C.c_int, [C.POINTER(MvsgiSweepArgs), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                             C.POINTER(C.c_int32)]),
     "mvsgi_sweep_octet_cost": (C.c_int, [C.POINTER(MvsgiSweepArgs), C.c_void_p, C.c_void_p]),
+    "mvsgi_sweep_grid": (C.c_int, [C.POINTER(MvsgiSweepArgs)]),
     "mvsgi_project_only_f32": (C.c_int, [C.POINTER(MvsgiProjectArgs), C.c_void_p]),
     "mvsgi_resample_f32": (C.c_int, [C.POINTER(MvsgiResampleArgs), C.c_void_p]),
     "mvsgi_mask_pitch_words": (C.c_int32, [C.c_int32]),

@@ -411,6 +411,7 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   kp.framesPerPass = p.cta_fb;
   kp.octOrder = p.oct_order ? a->octet_order : nullptr;
   kp.octUnits = p.oct_order ? a->order_units : 0;
+  kp.ctaTimes = reinterpret_cast<unsigned long long*>(a->cta_times_out);
   kp.wL = p.walk ? p.w_len : 0; kp.wSegs = p.walk ? p.w_segs : 0; kp.wNumSeg = p.walk ? p.w_num_seg : 0;
   if (p.direct) {  // the caller's channels-last tensor: element (b, cam, y, x, c) at b*s0 + cam*s1 + y*s3 + x*s4 + c
     kp.feat = a->feats;
@@ -609,6 +610,16 @@ int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* a, int32_t* runs_out, int32_
   *units_out = (num_oct + runs - 1) / runs;  // <= the default plan's octets per run, so the table fits
   *num_octets_out = num_oct;
   return MVSGI_OK;
+}
+
+int mvsgi_sweep_grid(const MvsgiSweepArgs* a) {
+  if (a == nullptr) return MVSGI_E_NULL;
+  MvsgiSweepArgs b = *a;
+  if (b.vol == nullptr) b.vol = reinterpret_cast<float*>(static_cast<uintptr_t>(256));
+  SweepPlan p;
+  const int rc = validate_and_plan(&b, &p);
+  if (rc != MVSGI_OK) return rc;
+  return p.tiled ? p.tiled_grid : p.grid;
 }
 
 int mvsgi_sweep_octet_cost(const MvsgiSweepArgs* a, int32_t* cost_out, void* stream) {

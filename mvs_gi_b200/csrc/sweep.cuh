@@ -65,6 +65,7 @@ struct SweepKP {
   // (-1 = empty slot); nullptr = the interleaved / contiguous assignment below
   const int* octOrder;
   int octUnits;
+  unsigned long long* ctaTimes;  // optional [gridDim.x][4] (MvsgiSweepArgs.cta_times_out)
   int wL, wSegs, wNumSeg;  // sweep_walk.cuh: segment length, segments per run, segments in the image
   // staged features: element (b, cam, cg, yp, xp, c) at feat[b*fsB + cam*fsCam + cg*fsCg + yp*fsY + xp*16 + c]
   const float* feat;
@@ -265,28 +266,25 @@ template <> struct VolT<true> { typedef uint16_t type; };
 // The record stride is odd, so the 8 records a warp reads at a time sit in 8 different banks.
 __host__ __device__ constexpr int entry_words(int cam) { return (2 + 3 * cam) | 1; }
 
-#ifdef MVSGI_CTA_TIMES  // diagnostic builds: (smid, start, end of the build, end) of every CTA, globaltimer ns
-__device__ unsigned long long g_cta_times[4 * 1024];
 MVSGI_DEV unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#endif
 
 template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16, bool DIRECT = false, bool VBF16 = false,
           int FB = 1>
 __global__ void __launch_bounds__(sweep_threads(FB), sweep_ctas(FB))
 sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   constexpr int NT = sweep_threads(FB);
-#ifdef MVSGI_CTA_TIMES
-  if (threadIdx.x == 0 && blockIdx.x < 1024) {
+  // MvsgiSweepArgs.cta_times_out: (SM id, start, end of the first table build, end) of every CTA in globaltimer
+  // nanoseconds — what ops.calibrated_octet_order() reads to find the SMs that run this kernel slower than the rest
+  if (kp.ctaTimes != nullptr && threadIdx.x == 0) {
     unsigned sm;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-    g_cta_times[4 * blockIdx.x] = sm;
-    g_cta_times[4 * blockIdx.x + 1] = gtimer();
+    kp.ctaTimes[4 * blockIdx.x] = sm;
+    kp.ctaTimes[4 * blockIdx.x + 1] = gtimer();
   }
-#endif
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int ES = entry_words(CAM);
   const int MP = kp.maxPairs;
@@ -423,9 +421,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       }
     }
 
-#ifdef MVSGI_CTA_TIMES
-    if (threadIdx.x == 0 && blockIdx.x < 1024) g_cta_times[4 * blockIdx.x + 2] = gtimer();
-#endif
+    if (kp.ctaTimes != nullptr && threadIdx.x == 0 && item == (int)blockIdx.x) kp.ctaTimes[4 * blockIdx.x + 2] = gtimer();
     // ---------------------------------------------------------------- sweep: frames outer, FB frames per pass
     // (FB > 1: host guarantees static masks and shared grids, so the table is the same for every frame)
     for (int b0 = 0; b0 < kp.B; b0 += FB) {
@@ -596,9 +592,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
     }
     // (the barrier above also protects the table: the next item's build overwrites it)
   }
-#ifdef MVSGI_CTA_TIMES
-  if (threadIdx.x == 0 && blockIdx.x < 1024) g_cta_times[4 * blockIdx.x + 3] = gtimer();
-#endif
+  if (kp.ctaTimes != nullptr && threadIdx.x == 0) kp.ctaTimes[4 * blockIdx.x + 3] = gtimer();
 }
 
 }  // namespace mvsgi

@@ -55,9 +55,3 @@ cudaError_t launch_sweep_cta_fb(int aggregate, int cams, const SweepKP& kp, cons
 }
 
 }  // namespace mvsgi
-
-#ifdef MVSGI_CTA_TIMES  // diagnostic builds only (scripts/build_variant.sh ctatimes -DMVSGI_CTA_TIMES): not in the C ABI header
-extern "C" int mvsgi_debug_cta_times(unsigned long long* host_out, int n_ctas) {
-  return (int)cudaMemcpyFromSymbol(host_out, mvsgi::g_cta_times, sizeof(unsigned long long) * 4 * n_ctas);
-}
-#endif

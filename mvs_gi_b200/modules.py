@@ -82,6 +82,10 @@ class _SweepBase(nn.Module):
         # 405 us at G16V and follow the count of (octet, candidate, camera loaded by the warp); dealt by that count they
         # lie within 345-353 us and the kernel ends 7 % earlier.  Set to False to keep the round-robin deal.
         self.balance_runs = True
+        # ... and corrected by measurement (ops.calibrated_octet_order): CTA slots that run the kernel slower than the
+        # rest get less work.  A dozen extra sweep launches at the first call with a given shape.
+        self.calibrate_runs = True
+        self.balance_report = None
         self._order_cache = None  # (key, int32 [runs, units] table or None)
         # Memory layout of the volume the sweep kernel writes.  False = the reference's NCDHW.  True = the same
         # [B,C,D,Ho,Wo] tensor with torch.channels_last_3d strides: the kernel then stores 512 contiguous bytes per
@@ -200,10 +204,14 @@ class _SweepBase(nn.Module):
             return c[1]
         if torch.cuda.is_current_stream_capturing():
             return None
-        call = ops.SweepCall(feats, None, None, bits, self._rig_blob, self._aggregate, Ho, Wo, D, describe_only=True,
-                             channels_last=self.vol_channels_last, feats_bf16=self.feats_bf16,
-                             mask_hw=(mask_h, mask_w) if mask_h > 0 else None, vol_bf16=self.vol_bf16)
-        order = ops.balanced_octet_order(call)
+        call = ops.SweepCall(feats, None, None, bits, self._rig_blob, self._aggregate, Ho, Wo, D,
+                             describe_only=not self.calibrate_runs, channels_last=self.vol_channels_last,
+                             feats_bf16=self.feats_bf16, mask_hw=(mask_h, mask_w) if mask_h > 0 else None,
+                             vol_bf16=self.vol_bf16)
+        if self.calibrate_runs:
+            order, self.balance_report = ops.calibrated_octet_order(call)
+        else:
+            order = ops.balanced_octet_order(call)
         self._order_cache = (key, order)
         return order
 

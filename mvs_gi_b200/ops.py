@@ -233,11 +233,13 @@ class SweepCall:
         abi.check(rc, "mvsgi_sweep_f32")
 
 
-def lpt_assign(cost, runs: int, units: int):
+def lpt_assign(cost, runs: int, units: int, slowdown=None):
     """Deal octets (index = position in `cost`) to `runs` runs of at most `units` slots so that the runs' total costs
     are as equal as their equal cardinality allows: longest-processing-time-first in rounds — the octets in descending
     cost, `runs` at a time, the dearest of a round to the run that is lightest so far — so every run gets one octet per
     round and the spread left after a round is at most the spread of costs inside it.
+    `slowdown` [runs]: relative time per unit of cost of the CTA that will sweep each run (1 = nominal; a run on an SM
+    that takes 8 % longer has 1.08): the loads are equalised in time, load * slowdown, instead of in cost.
     -> int32 [runs, units], -1 = empty slot; every octet appears exactly once."""
     import numpy as np
 
@@ -245,16 +247,21 @@ def lpt_assign(cost, runs: int, units: int):
     n = int(cost.size)
     if runs * units < n:
         raise ValueError("more octets than slots")
+    slow = np.ones(runs) if slowdown is None else np.asarray(slowdown, dtype=np.float64)
+    if slow.shape != (runs,) or not np.all(slow > 0):
+        raise ValueError("slowdown must hold one positive factor per run")
     order = np.full((runs, units), -1, dtype=np.int32)
-    load = np.zeros(runs, dtype=np.int64)
+    load = np.zeros(runs, dtype=np.float64)
     desc = np.argsort(-cost, kind="stable")
     for k in range(units):
         chunk = desc[k * runs:(k + 1) * runs]
         if chunk.size == 0:
             break
-        light = np.argsort(load, kind="stable")[:chunk.size]  # lightest runs first
+        # lightest runs first; a slow run counts as if it already carried its handicap over the rounds still to come
+        ahead = load + (slow - 1.0) * (units - k) * float(cost[chunk].mean()) if slowdown is not None else load
+        light = np.argsort(ahead, kind="stable")[:chunk.size]
         order[light, k] = chunk
-        load[light] += cost[chunk]
+        load[light] += cost[chunk] * slow[light]
     # compact: empty slots (only possible in the last, partial round) stay at the end of their run by construction
     return order
 
@@ -279,6 +286,80 @@ def balanced_octet_order(call: "SweepCall") -> Optional[Tensor]:
     abi.check(rc, "mvsgi_sweep_octet_cost")
     order = lpt_assign(cost.cpu().numpy(), runs.value, units.value)
     return torch.from_numpy(order).to(call.device)
+
+
+def cta_times(call: "SweepCall", launches: int = 3):
+    """(sm [ctas], microseconds [launches, ctas]) of the sweep kernel's CTAs for `call` (MvsgiSweepArgs.cta_times_out),
+    after one warm-up launch.  Synchronises."""
+    import numpy as np
+
+    n = call.lib.mvsgi_sweep_grid(C.byref(call.args))
+    if n < 0:
+        abi.check(int(n), "mvsgi_sweep_grid")
+    buf = torch.zeros((n, 4), dtype=torch.int64, device=call.device)
+    call.args.cta_times_out = buf.data_ptr()
+    try:
+        call.run()
+        out = []
+        for _ in range(launches):
+            call.run()
+            torch.cuda.synchronize(call.device)
+            t = buf.cpu().numpy()
+            out.append((t[:, 3] - t[:, 1]) / 1e3)
+        sm = t[:, 0].copy()
+    finally:
+        call.args.cta_times_out = None
+    return sm, np.stack(out)
+
+
+def calibrated_octet_order(call: "SweepCall", rounds: int = 3, threshold: float = 0.015):
+    """balanced_octet_order(), then a few measured corrections: the sweep is run with the table and per-CTA timestamps
+    (MvsgiSweepArgs.cta_times_out); a CTA that finishes later than the median — on the B200s measured the same handful
+    of CTA slots does, launch after launch, by 5-8 %: the placement of a full one-wave grid on the SMs repeats — gets
+    the ratio as the `slowdown` of its run, and the octets are dealt again (ops.lpt_assign).  Up to `rounds` such
+    steps; the table with the shortest measured kernel time is returned, with a small report — never worse than the
+    balanced table it starts from.  `call` must be a complete SweepCall (its volume is overwritten); a dozen launches
+    and synchronisations — once per (device, rig, masks, shape), outside any timed or captured region."""
+    import numpy as np
+
+    order = balanced_octet_order(call)
+    if order is None:
+        return None, {"calibrated": False, "why": "the problem is not swept as one item per resident CTA"}
+    saved = (call.args.octet_order, call.args.order_runs, call.args.order_units)
+    try:
+        runs, units = order.shape
+        noct = int((order >= 0).sum())
+        cost_t = torch.empty((noct,), dtype=torch.int32, device=call.device)
+        with torch.cuda.device(call.device):
+            abi.check(call.lib.mvsgi_sweep_octet_cost(C.byref(call.args), cost_t.data_ptr(), _stream_ptr(call.device)),
+                      "mvsgi_sweep_octet_cost")
+        cost = cost_t.cpu().numpy()
+        call.set_octet_order(order)
+        _, us = cta_times(call)
+        best, best_us = order, float(us.max(axis=1).min())
+        report = {"calibrated": False, "kernel_us_balanced": best_us, "kernel_us_rounds": []}
+        slow = np.ones(runs)
+        for _ in range(rounds):
+            med = np.median(us, axis=0)                   # per CTA = per run, over the launches
+            ratio = med / float(np.median(med))
+            step = np.where(np.abs(ratio - 1.0) > threshold, np.clip(ratio, 0.95, 1.12), 1.0)
+            if np.all(step == 1.0):
+                break
+            slow = slow * step
+            slow = slow / np.median(slow)
+            cand = torch.from_numpy(lpt_assign(cost, runs, units, slow)).to(call.device)
+            call.set_octet_order(cand)
+            _, us = cta_times(call)
+            k_us = float(us.max(axis=1).min())
+            report["kernel_us_rounds"].append(k_us)
+            if k_us < best_us:
+                best, best_us = cand, k_us
+                report["calibrated"] = True
+        report["kernel_us"] = best_us
+        report["runs_slower_than_2pct"] = int((slow > 1.02).sum())
+        return best, report
+    finally:
+        call.args.octet_order, call.args.order_runs, call.args.order_units = saved
 
 
 def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,

@@ -1,6 +1,6 @@
-"""Diagnostic (run on the GPU box with a -DMVSGI_CTA_TIMES build selected by MVSGI_B200_LIB): when does every CTA of the
-sweep start, finish its table build and finish — which SMs / runs are the late ones?
-usage: MVSGI_B200_LIB=.../libmvsgi_b200_ctatimes.so python scripts/cta_times.py WORKLOAD BATCH [balance 0|1]"""
+"""Diagnostic (GPU box): when does every CTA of the sweep start, finish its table build and finish
+(MvsgiSweepArgs.cta_times_out) — which SMs / runs are the late ones?
+usage: python scripts/cta_times.py WORKLOAD BATCH [0 = round-robin octets | 1 = cost-balanced | 2 = + measured correction]"""
 import ctypes as C
 import json
 import os
@@ -14,7 +14,6 @@ import torch
 from mvs_gi_b200 import abi, ops, synthetic
 
 name, B = sys.argv[1], int(sys.argv[2])
-bal = len(sys.argv) > 3 and sys.argv[3] == "1"
 w = synthetic.WORKLOADS[name]
 dev = torch.device("cuda:0")
 rig_blob = ops.rig_to_blob(w.rig().to_struct())
@@ -25,19 +24,37 @@ sets = [torch.randn((B, w.num_cams, Hf, Wf, w.feat_chs), device=dev, generator=g
 calls = [ops.SweepCall(f, None, None, masks, rig_blob, abi.AGG_STD, w.cv_hw[0], w.cv_hw[1], len(w.dist_list),
                        channels_last=True, mask_hw=w.mask_hw) for f in sets]
 order = None
-if bal:
+mode = sys.argv[3] if len(sys.argv) > 3 else "0"   # 0 = round-robin octets, 1 = cost-balanced, 2 = + measured correction
+if mode == "1":
     order = ops.balanced_octet_order(calls[0])
+elif mode == "2":
+    order, rep = ops.calibrated_octet_order(calls[0])
+    print("calibration:", json.dumps(rep))
+bal = order is not None
+if bal:
     for c in calls:
         c.set_octet_order(order)
 lib = abi.load_library()
-for i in range(7):
+for i in range(6):
     calls[i % 3].run()
 torch.cuda.synchronize()
-n = 296
-buf = (C.c_ulonglong * (4 * n))()
-assert lib.mvsgi_debug_cta_times(buf, n) == 0
-t = np.array(buf[:], dtype=np.int64).reshape(n, 4)
-t = t[t[:, 1] > 0]
+n = lib.mvsgi_sweep_grid(C.byref(calls[0].args))
+bufs = [torch.zeros((n, 4), dtype=torch.int64, device=dev) for _ in calls]
+for c, b_ in zip(calls, bufs):
+    c.args.cta_times_out = b_.data_ptr()
+# which CTA is the last one, launch after launch: the same run, the same SM, or a different one every time?
+last = []
+for i in range(8):
+    calls[i % 3].run()
+    torch.cuda.synchronize()
+    tt = bufs[i % 3].cpu().numpy()
+    d_ = (tt[:, 3] - tt[:, 1]) / 1e3
+    top = np.argsort(-d_)[:3]
+    last.append([(int(j), int(tt[j, 0]), round(float(d_[j]), 1)) for j in top] + [round(float(np.median(d_)), 1)])
+print("slowest three (run, sm, us) + median per launch:")
+for l in last:
+    print("  ", l)
+t = tt
 sm, t0, tb, t1 = t[:, 0], t[:, 1], t[:, 2], t[:, 3]
 start = t0.min()
 dur = (t1 - t0) / 1e3
@@ -61,7 +78,7 @@ for lo in range(0, 160, 16):
     sel = (sm_dur[:, 0] >= lo) & (sm_dur[:, 0] < lo + 16)
     if sel.any():
         print(f"  SM {lo:3d}-{lo + 15:3d}: mean {sm_dur[sel, 1].mean():7.1f} us  max {sm_dur[sel, 1].max():7.1f}")
-np.savez(f"gpurun_out/cta_times_{name}_{B}_{int(bal)}.npz", t=t, order=(order.cpu().numpy() if order is not None else np.zeros(0)))
+np.savez(f"gpurun_out/cta_times_{name}_{B}_{mode}.npz", t=t, order=(order.cpu().numpy() if order is not None else np.zeros(0)))
 idx = np.arange(len(dur))
 print("corr(duration, blockIdx) =", float(np.corrcoef(idx, dur)[0, 1]))
 if order is not None or True:

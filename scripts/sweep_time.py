@@ -30,7 +30,11 @@ calls = [ops.SweepCall(f, None, None, masks if agg == abi.AGG_STD else None, rig
                        channels_last=True, mask_hw=w.mask_hw) for f in sets]
 balanced = False
 if os.environ.get("BALANCE", "1") != "0":  # cost-balanced runs (ops.balanced_octet_order), computed once
-    order = ops.balanced_octet_order(calls[0])
+    if os.environ.get("BALANCE") == "2":  # + measured correction
+        order, rep = ops.calibrated_octet_order(calls[0])
+        print("calibration:", json.dumps(rep), flush=True)
+    else:
+        order = ops.balanced_octet_order(calls[0])
     if order is not None:
         balanced = True
         for c in calls:

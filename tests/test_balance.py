@@ -157,3 +157,53 @@ def test_module_path_balances_once_and_matches(dev):
         m.balance_runs = False
         v3 = m.sweep(feats, None, None, None)
     assert torch.equal(v1, v2) and torch.equal(v1, v3)
+
+
+def test_lpt_assign_gives_slow_runs_less():
+    """slowdown: a run on an SM that needs 8 % longer per unit of cost gets about 8 % less cost."""
+    from mvs_gi_b200 import ops
+
+    rng = np.random.default_rng(5)
+    cost = np.where(rng.random(3200) < 0.3, 64, rng.integers(300, 560, 3200))
+    slow = np.ones(296)
+    slow[[7, 111, 290]] = 1.08
+    order = ops.lpt_assign(cost, 296, 11, slow)
+    used = order[order >= 0]
+    assert np.array_equal(np.sort(used), np.arange(3200))
+    load = np.array([cost[o[o >= 0]].sum() for o in order], float)
+    t = load * slow
+    assert t.max() / t.mean() < 1.03
+    assert np.all(load[[7, 111, 290]] < 0.95 * load.mean())
+    with pytest.raises(ValueError):
+        ops.lpt_assign(cost, 296, 11, np.ones(5))
+
+
+@pytest.mark.gpu
+def test_cta_times_and_calibrated_order(dev):
+    """cta_times_out: one row per CTA (SM id, start <= end of build <= end); the calibrated table is a valid table (the
+    same volume bit for bit) and the report says what was measured."""
+    from mvs_gi_b200 import abi, ops, synthetic
+
+    w = synthetic.WORKLOADS["G16V"]
+    B = 8
+    feats = _nhwc(torch.randn((B, w.num_cams, w.feat_chs, *w.feat_hw), device=dev))
+    blob = ops.rig_to_blob(w.rig().to_struct())
+    bits = ops.pack_masks(torch.from_numpy(synthetic.fisheye_footprint_masks(w)).to(dev)[None])
+    mk = lambda: ops.SweepCall(feats, None, None, bits, blob, abi.AGG_STD, w.cv_hw[0], w.cv_hw[1], len(w.dist_list),
+                               channels_last=True, mask_hw=tuple(w.mask_hw))
+    plain, cal = mk(), mk()
+    plain.run()
+    sm, us = ops.cta_times(plain, launches=2)
+    assert us.shape[0] == 2 and us.shape[1] == sm.shape[0] > 100
+    assert np.all(us > 1.0) and np.all(us < 5e3) and sm.max() < 512 and len(np.unique(sm)) > 100
+    assert plain.args.cta_times_out is None, "the timing buffer is detached again"
+    order, report = ops.calibrated_octet_order(cal)
+    assert order is not None and "kernel_us_balanced" in report and report["kernel_us"] <= report["kernel_us_balanced"]
+    o = order.cpu().numpy()
+    assert np.array_equal(np.sort(o[o >= 0]), np.arange(w.cv_hw[0] * w.cv_hw[1] // 8))
+    cal.set_octet_order(order)
+    cal.vol.zero_()
+    cal.run()
+    plain.run()
+    torch.cuda.synchronize()
+    assert torch.equal(plain.vol.view(torch.int32), cal.vol.view(torch.int32))
