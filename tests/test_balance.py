@@ -172,7 +172,7 @@ def test_lpt_assign_gives_slow_runs_less():
     assert np.array_equal(np.sort(used), np.arange(3200))
     load = np.array([cost[o[o >= 0]].sum() for o in order], float)
     t = load * slow
-    assert t.max() / t.mean() < 1.03
+    assert t.max() / np.median(t) < 1.01
     assert np.all(load[[7, 111, 290]] < 0.95 * load.mean())
     with pytest.raises(ValueError):
         ops.lpt_assign(cost, 296, 11, np.ones(5))
