@@ -218,9 +218,10 @@ int64_t mvsgi_sweep_workspace_bytes(const MvsgiSweepArgs* args);
 /* Enqueue staging (if needed) + the fused sweep/aggregate kernel. */
 int mvsgi_sweep_f32(const MvsgiSweepArgs* args, void* cuda_stream);
 
-/* Shape of the octet_order table this problem accepts: runs = resident CTAs of the sweep (or fewer for tiny images),
- * units = octets per run, num_octets = ceil(out_h * out_w / 8).  MVSGI_E_UNSUPPORTED when the problem is not swept as
- * one item per resident CTA (candidate chunks, several waves, per-frame grids): leave octet_order NULL then.
+/* Shape of the octet_order table this problem accepts: runs = resident CTAs of the sweep (fewer for tiny images; k times
+ * as many when the tap table of 1/CTAs of the image does not fit one pass: CTA c then sweeps runs c, c + grid, ...,
+ * grid = mvsgi_sweep_grid), units = octets per run, num_octets = ceil(out_h * out_w / 8).  MVSGI_E_UNSUPPORTED when the
+ * candidates are swept in chunks (more than 16) or the grids are per-frame: leave octet_order NULL then.
  * args->octet_order is ignored; args->vol and args->workspace may be NULL (nothing is written). */
 int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* args, int32_t* runs_out, int32_t* units_out, int32_t* num_octets_out);
 

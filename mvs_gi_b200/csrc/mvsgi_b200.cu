@@ -315,19 +315,22 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   p->group_px = env_int("MVSGI_GROUP_PX", p->interleave ? p->run_len : 32);
   if (p->group_px < 1) p->group_px = 1;
   p->grid_target = grid_target;
-  p->one_item_per_cta = p->num_chunks == 1 && unit == 1 && p->num_items <= grid_target && !p->per_frame_grids && !p->tiled;
+  // the plans a caller's octet_order can replace: all candidates in one chunk, single octets; one item per resident
+  // CTA, or k whole waves of items (CTA c sweeps items c, c + grid, ...)
+  p->one_item_per_cta = p->num_chunks == 1 && unit == 1 && !p->per_frame_grids && !p->tiled;
   p->oct_order = false;
   if (a->octet_order != nullptr) {  // cost-balanced runs: same table budget, the caller's assignment of octets to runs
     const int64_t cap = budget / (8 * per_px);
-    if (!p->one_item_per_cta || a->order_runs < 1 || a->order_runs > grid_target || a->order_units < 1 ||
-        a->order_units > cap || (int64_t)a->order_runs * a->order_units < num_oct)
+    if (!p->one_item_per_cta || a->order_runs < 1 || a->order_runs > 64 * grid_target || a->order_units < 1 ||
+        a->order_units > cap || (int64_t)a->order_runs * a->order_units < num_oct ||
+        (a->order_runs > grid_target && a->order_runs % grid_target != 0))
       return MVSGI_E_UNSUPPORTED;
     p->oct_order = true;
     p->num_runs = a->order_runs;
     p->run_len = 8 * a->order_units;
     p->num_items = p->num_runs;
     p->max_pairs = p->run_len * dch;
-    p->grid = p->num_items;
+    p->grid = p->num_items < grid_target ? p->num_items : grid_target;
     p->group_px = p->run_len;
   }
   p->smem_bytes = align_up((int64_t)p->max_pairs * per_pair + (int64_t)p->run_len * 12 + 16, 16);
@@ -605,9 +608,11 @@ int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* a, int32_t* runs_out, int32_
   if (rc != MVSGI_OK) return rc;
   if (!p.one_item_per_cta) return MVSGI_E_UNSUPPORTED;
   const int num_oct = (a->out_h * a->out_w + 7) / 8;
-  const int runs = num_oct < p.grid_target ? num_oct : p.grid_target;
+  // k whole waves of runs, k as in the default plan (its runs fit the table; more, smaller runs fit as well)
+  const int waves = (p.num_runs + p.grid_target - 1) / p.grid_target;
+  const int runs = num_oct < p.grid_target ? num_oct : waves * p.grid_target;
   *runs_out = runs;
-  *units_out = (num_oct + runs - 1) / runs;  // <= the default plan's octets per run, so the table fits
+  *units_out = (num_oct + runs - 1) / runs;
   *num_octets_out = num_oct;
   return MVSGI_OK;
 }

@@ -284,8 +284,30 @@ def balanced_octet_order(call: "SweepCall") -> Optional[Tensor]:
     if rc == abi.E_UNSUPPORTED:
         return None
     abi.check(rc, "mvsgi_sweep_octet_cost")
-    order = lpt_assign(cost.cpu().numpy(), runs.value, units.value)
+    order = deal_octets(cost.cpu().numpy(), runs.value, units.value, _sweep_ctas(call, runs.value))
     return torch.from_numpy(order).to(call.device)
+
+
+def _sweep_ctas(call: "SweepCall", runs: int) -> int:
+    """CTAs of the sweep kernel for a table of `runs` runs: all of them resident, CTA c sweeps runs c, c + ctas, ..."""
+    n = call.lib.mvsgi_sweep_grid(C.byref(call.args))
+    if n < 0:
+        abi.check(int(n), "mvsgi_sweep_grid")
+    return min(int(n), runs)
+
+
+def deal_octets(cost, runs: int, units: int, ctas: int, slowdown=None):
+    """The [runs, units] table for `ctas` CTAs that each sweep runs c, c + ctas, ...: lpt_assign over the CTAs (a CTA's
+    time is the sum over its runs; `slowdown` per CTA), each CTA's octets then cut into its runs in order."""
+    import numpy as np
+
+    if runs <= ctas:
+        return lpt_assign(cost, runs, units, slowdown)
+    if runs % ctas != 0:
+        raise ValueError("runs must be whole waves of the CTAs")
+    k = runs // ctas
+    per_cta = lpt_assign(cost, ctas, k * units, slowdown)          # [ctas, k * units], -1 only at the end of a row
+    return np.ascontiguousarray(per_cta.reshape(ctas, k, units).transpose(1, 0, 2).reshape(runs, units))
 
 
 def cta_times(call: "SweepCall", launches: int = 3):
@@ -336,18 +358,19 @@ def calibrated_octet_order(call: "SweepCall", rounds: int = 3, threshold: float 
         cost = cost_t.cpu().numpy()
         call.set_octet_order(order)
         _, us = cta_times(call)
+        ctas = us.shape[1]
         best, best_us = order, float(us.max(axis=1).min())
         report = {"calibrated": False, "kernel_us_balanced": best_us, "kernel_us_rounds": []}
-        slow = np.ones(runs)
+        slow = np.ones(ctas)
         for _ in range(rounds):
-            med = np.median(us, axis=0)                   # per CTA = per run, over the launches
+            med = np.median(us, axis=0)                   # per CTA, over the launches
             ratio = med / float(np.median(med))
             step = np.where(np.abs(ratio - 1.0) > threshold, np.clip(ratio, 0.95, 1.12), 1.0)
             if np.all(step == 1.0):
                 break
             slow = slow * step
             slow = slow / np.median(slow)
-            cand = torch.from_numpy(lpt_assign(cost, runs, units, slow)).to(call.device)
+            cand = torch.from_numpy(deal_octets(cost, runs, units, ctas, slow)).to(call.device)
             call.set_octet_order(cand)
             _, us = cta_times(call)
             k_us = float(us.max(axis=1).min())
@@ -356,7 +379,7 @@ def calibrated_octet_order(call: "SweepCall", rounds: int = 3, threshold: float 
                 best, best_us = cand, k_us
                 report["calibrated"] = True
         report["kernel_us"] = best_us
-        report["runs_slower_than_2pct"] = int((slow > 1.02).sum())
+        report["ctas_slower_than_2pct"] = int((slow > 1.02).sum())
         return best, report
     finally:
         call.args.octet_order, call.args.order_runs, call.args.order_units = saved
