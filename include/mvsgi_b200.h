@@ -219,11 +219,12 @@ int64_t mvsgi_sweep_workspace_bytes(const MvsgiSweepArgs* args);
 int mvsgi_sweep_f32(const MvsgiSweepArgs* args, void* cuda_stream);
 
 /* Shape of the octet_order table this problem accepts: runs = resident CTAs of the sweep (fewer for tiny images; k times
- * as many when the tap table of 1/CTAs of the image does not fit one pass: CTA c then sweeps runs c, c + grid, ...,
- * grid = mvsgi_sweep_grid), units = octets per run, num_octets = ceil(out_h * out_w / 8).  MVSGI_E_UNSUPPORTED when the
+ * as many when the tap table of 1/CTAs of the image does not fit one pass: CTA c then sweeps runs c, c + ctas, ...,
+ * ctas = the CTAs the sweep is launched with once the table is attached), units = octets per run, num_octets = ceil(out_h * out_w / 8).  MVSGI_E_UNSUPPORTED when the
  * candidates are swept in chunks (more than 16) or the grids are per-frame: leave octet_order NULL then.
  * args->octet_order is ignored; args->vol and args->workspace may be NULL (nothing is written). */
-int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* args, int32_t* runs_out, int32_t* units_out, int32_t* num_octets_out);
+int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* args, int32_t* runs_out, int32_t* units_out, int32_t* num_octets_out,
+                              int32_t* ctas_out);
 
 /* CTAs the sweep kernel of this problem is launched with (rows of cta_times_out); negative = error. */
 int mvsgi_sweep_grid(const MvsgiSweepArgs* args);

@@ -186,7 +186,7 @@ EXPORTS = {
     "mvsgi_sweep_f32": (C.c_int, [C.POINTER(MvsgiSweepArgs), C.c_void_p]),
     "mvsgi_sweep_launch_count": (C.c_int, [C.POINTER(MvsgiSweepArgs)]),
     "mvsgi_sweep_balance_shape": (C.c_int, [C.POINTER(MvsgiSweepArgs), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
-                                            C.POINTER(C.c_int32)]),
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mvsgi_sweep_octet_cost": (C.c_int, [C.POINTER(MvsgiSweepArgs), C.c_void_p, C.c_void_p]),
     "mvsgi_sweep_grid": (C.c_int, [C.POINTER(MvsgiSweepArgs)]),
     "mvsgi_project_only_f32": (C.c_int, [C.POINTER(MvsgiProjectArgs), C.c_void_p]),

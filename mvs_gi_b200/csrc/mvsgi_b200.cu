@@ -597,8 +597,10 @@ int64_t mvsgi_sweep_workspace_bytes(const MvsgiSweepArgs* a) {
   return rc != MVSGI_OK ? (int64_t)rc : p.total_bytes;
 }
 
-int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* a, int32_t* runs_out, int32_t* units_out, int32_t* num_octets_out) {
-  if (a == nullptr || runs_out == nullptr || units_out == nullptr || num_octets_out == nullptr) return MVSGI_E_NULL;
+int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* a, int32_t* runs_out, int32_t* units_out, int32_t* num_octets_out,
+                              int32_t* ctas_out) {
+  if (a == nullptr || runs_out == nullptr || units_out == nullptr || num_octets_out == nullptr || ctas_out == nullptr)
+    return MVSGI_E_NULL;
   MvsgiSweepArgs b = *a;
   b.octet_order = nullptr;
   b.order_runs = b.order_units = 0;
@@ -614,6 +616,7 @@ int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* a, int32_t* runs_out, int32_
   *runs_out = runs;
   *units_out = (num_oct + runs - 1) / runs;
   *num_octets_out = num_oct;
+  *ctas_out = runs < p.grid_target ? runs : p.grid_target;
   return MVSGI_OK;
 }
 

@@ -273,8 +273,8 @@ def balanced_octet_order(call: "SweepCall") -> Optional[Tensor]:
     synchronisation — meant to be done once per (rig, masks, shape) and cached, like the packed masks.  None when the
     problem is not swept as one item per resident CTA (high-D, per-frame grids): the default assignment stays."""
     lib = call.lib
-    runs, units, noct = C.c_int32(), C.c_int32(), C.c_int32()
-    rc = lib.mvsgi_sweep_balance_shape(C.byref(call.args), C.byref(runs), C.byref(units), C.byref(noct))
+    runs, units, noct, ctas = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    rc = lib.mvsgi_sweep_balance_shape(C.byref(call.args), C.byref(runs), C.byref(units), C.byref(noct), C.byref(ctas))
     if rc == abi.E_UNSUPPORTED:
         return None
     abi.check(rc, "mvsgi_sweep_balance_shape")
@@ -284,16 +284,8 @@ def balanced_octet_order(call: "SweepCall") -> Optional[Tensor]:
     if rc == abi.E_UNSUPPORTED:
         return None
     abi.check(rc, "mvsgi_sweep_octet_cost")
-    order = deal_octets(cost.cpu().numpy(), runs.value, units.value, _sweep_ctas(call, runs.value))
+    order = deal_octets(cost.cpu().numpy(), runs.value, units.value, ctas.value)
     return torch.from_numpy(order).to(call.device)
-
-
-def _sweep_ctas(call: "SweepCall", runs: int) -> int:
-    """CTAs of the sweep kernel for a table of `runs` runs: all of them resident, CTA c sweeps runs c, c + ctas, ..."""
-    n = call.lib.mvsgi_sweep_grid(C.byref(call.args))
-    if n < 0:
-        abi.check(int(n), "mvsgi_sweep_grid")
-    return min(int(n), runs)
 
 
 def deal_octets(cost, runs: int, units: int, ctas: int, slowdown=None):

@@ -83,8 +83,8 @@ idx = np.arange(len(dur))
 print("corr(duration, blockIdx) =", float(np.corrcoef(idx, dur)[0, 1]))
 if order is not None or True:
     # cost of each run under the assignment in use
-    runs, units, noct = C.c_int32(), C.c_int32(), C.c_int32()
-    lib.mvsgi_sweep_balance_shape(C.byref(calls[0].args), C.byref(runs), C.byref(units), C.byref(noct))
+    runs, units, noct, nctas = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    lib.mvsgi_sweep_balance_shape(C.byref(calls[0].args), C.byref(runs), C.byref(units), C.byref(noct), C.byref(nctas))
     cost = torch.empty((noct.value,), dtype=torch.int32, device=dev)
     lib.mvsgi_sweep_octet_cost(C.byref(calls[0].args), cost.data_ptr(), torch.cuda.current_stream().cuda_stream)
     c = cost.cpu().numpy().astype(np.int64)
