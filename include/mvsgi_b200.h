@@ -303,8 +303,11 @@ int mvsgi_softargmin_f32(const MvsgiSoftArgminArgs* args, void* cuda_stream);
  * SphericalSweep.sweep (spherical_sweep.py:38-68) incl. the sampler's gather backward (backports.py:76-86).
  * Of `fwd`, the fields vol, valid_out, peer_vols, num_peers, flags, workspace and workspace_bytes are ignored
  * (cand_offset / vol_num_cands are honoured: grad_vol is then the full [B, Cout, vol_num_cands, Ho, Wo] tensor).
- * The call re-stages feats and masks, accumulates with vector atomics into a staged gradient image and writes
- * grad_feats (overwritten, not accumulated).  Summation order is not deterministic (fp32 atomics). */
+ * The backward runs the sweep kernel's own work decomposition with a scatter (vector atomics) in place of the store.
+ * Dense channels-last feats (whole 16-channel groups, the layout the forward taps in place) with grad_feats of the
+ * same strides: grad_feats is cleared and accumulated into directly (memset + one kernel).  Otherwise feats are staged
+ * as in the forward, the gradient is accumulated in a staged image and un-staged into grad_feats (any strides).
+ * grad_feats is overwritten, not accumulated.  Summation order is not deterministic (fp32 atomics). */
 typedef struct MvsgiSweepBwdArgs {
   uint32_t struct_size; /* = sizeof(MvsgiSweepBwdArgs) */
   uint32_t flags;       /* 0 */

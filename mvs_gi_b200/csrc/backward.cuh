@@ -10,199 +10,21 @@
 //   soft-argmin    softmax backward p_d (G_d - sum_e p_e G_e), G_d = g_norm_costs_d + g_inv_dist * inv_dist_idx_d,
 //                  followed by the adjoint of the bilinear upsample (distance_regressor.py:51-80)
 //
-// The sampler adjoint is a scatter-add.  It accumulates into a zero-initialised gradient image with the SAME
-// channels-last padded layout as the staged features ([B][CAM][CG][Hf+3][Wf+2][16]), so a tap's 16 channels are four
-// 16-byte vector reductions (red.global.add.v4.f32, one per lane of the quad that owns the voxel) and the padding taps
-// need no test: their sums land in the frame and are never read back.  unstage_grad_kernel then writes the interior
-// to grad_feats in the caller's layout.
+// The sampler adjoint is a scatter-add.  The sweep's backward is the BWD instantiation of sweep_kernel (sweep.cuh): the
+// forward's work decomposition — tap table in shared memory, built once for all frames, mask lookups, frame loop —
+// with the scatter in place of the store.  It accumulates into a zero-initialised gradient image with the layout of
+// the features it taps: the caller's dense channels-last grad_feats directly (2 launches: memset + kernel), or, for
+// NCHW features, the staged layout ([B][CAM][CG][Hf+3][Wf+2][16]), where the padding taps need no test (their sums land
+// in the frame and are never read back) and unstage_grad_kernel then writes the interior to grad_feats.  A tap's 16
+// channels are four 16-byte vector reductions (red.global.add.v4.f32, one per lane of the quad that owns the voxel).
+// This file keeps the un-staging kernel and the general soft-argmin backward.
 #pragma once
 #include "softargmin.cuh"
 #include "sweep.cuh"
 
 namespace mvsgi {
 
-MVSGI_DEV void red_add4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-struct SweepBwdKP {
-  SweepKP f;             // forward problem (feat = staged features, mbits = packed masks; vol unused)
-  const float* gradVol;  // [B, Cout, Dvol, Ho, Wo]
-  float* gradStage;      // zero-initialised, staged layout
-  // geometry shared by the frames (fused projection or shared grids): per (candidate, pixel, camera) the tap offset,
-  // frac x, frac y and the mask lookup info, evaluated once by sweep_backward_geom_kernel instead of once per frame
-  // in every quad; nullptr = evaluate in the backward kernel (per-frame grids)
-  const uint4* geom;
-};
-
-// [D][P][CAM] entries: (tap offset incl. the camera's image, frac x, frac y, mask info | kMaskNone)
-template <int CAM, int AGG>
-__global__ void __launch_bounds__(128)
-sweep_backward_geom_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig, uint4* __restrict__ out) {
-  const int pix = blockIdx.x * 128 + threadIdx.x;
-  if (pix >= kp.P) return;
-  const int d = blockIdx.y;
-  const int h = pix / kp.Wo, w = pix - h * kp.Wo;
-  float rx = 0.f, ry = 0.f, rz = 0.f;
-  if (kp.gridMode == MVSGI_GRID_PROJECT) cv_ray(rig, h, w, rx, ry, rz);
-#pragma unroll
-  for (int cam = 0; cam < CAM; ++cam) {
-    float gx, gy;
-    bool gvalid = true;
-    if (kp.gridMode == MVSGI_GRID_PROJECT) {
-      float x, y, z;
-      to_camera(rig.cams[cam], rx, ry, rz, rig.dist[d], x, y, z);
-      gvalid = project(rig.cams[cam], x, y, z, gx, gy);
-    } else {
-      const float2 g = __ldg(reinterpret_cast<const float2*>(kp.grids + cam * kp.gsCam + d * kp.gsD + h * kp.gsY +
-                                                               w * kp.gsX));
-      gx = g.x;
-      gy = g.y;
-      if (AGG == MVSGI_AGG_STD) gvalid = __ldg(kp.gmask + cam * kp.gmCam + d * kp.gmD + h * kp.gmY + w * kp.gmX) != 0;
-    }
-    int off;
-    float lx, ly;
-    make_entry(kp, gx, gy, off, lx, ly);
-    uint32_t info = kMaskNone;
-    if (AGG == MVSGI_AGG_STD && gvalid) info = make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch);
-    out[((long long)d * kp.P + pix) * CAM + cam] =
-        make_uint4((uint32_t)(off + cam * kp.fsCam), __float_as_uint(lx), __float_as_uint(ly), info);
-  }
-}
-
-constexpr int kBwdThreads = 256;  // 64 quads = 64 voxels per block
-
-// grid: (ceil(P / 64), D, B).  A quad of 4 lanes owns voxel (b, d, pixel); lane q evaluates the geometry and the mask
-// test of camera q and the quad shares them with shuffles; then every lane handles its 4 channels of each group.
-template <int CAM, int AGG>
-__global__ void __launch_bounds__(kBwdThreads)
-sweep_backward_kernel(const SweepBwdKP kb, const __grid_constant__ MvsgiRig rig) {
-  const SweepKP& kp = kb.f;
-  const int lane = threadIdx.x & 31, q = lane & 3;
-  const int pixRaw = blockIdx.x * (kBwdThreads / 4) + (threadIdx.x >> 2);
-  const bool act = pixRaw < kp.P;
-  const int pix = act ? pixRaw : kp.P - 1;
-  const int d = blockIdx.y, b = blockIdx.z;
-  const int h = pix / kp.Wo, w = pix - h * kp.Wo;
-  const int HW = kp.P;
-  const unsigned qmask = 0xFu << (lane & ~3);
-
-  // ---- lane q: camera q
-  int off = kp.zeroOff;
-  float lx = 0.f, ly = 0.f;
-  uint32_t bit = 0;
-  if (q < CAM) {
-    uint32_t info = kMaskNone;
-    if (kb.geom != nullptr) {
-      const uint4 e = __ldg(kb.geom + ((long long)d * kp.P + pix) * CAM + q);
-      off = (int)e.x;
-      lx = __uint_as_float(e.y);
-      ly = __uint_as_float(e.z);
-      info = e.w;
-    } else {
-      float gx, gy;
-      bool gvalid = true;
-      if (kp.gridMode == MVSGI_GRID_PROJECT) {
-        float rx, ry, rz, x, y, z;
-        cv_ray(rig, h, w, rx, ry, rz);
-        to_camera(rig.cams[q], rx, ry, rz, rig.dist[d], x, y, z);
-        gvalid = project(rig.cams[q], x, y, z, gx, gy);
-      } else {
-        const long long bb = kp.perFrameGrids ? b : 0;
-        const float2 g = __ldg(reinterpret_cast<const float2*>(kp.grids + bb * kp.gsB + q * kp.gsCam + d * kp.gsD +
-                                                                 h * kp.gsY + w * kp.gsX));
-        gx = g.x;
-        gy = g.y;
-        if (AGG == MVSGI_AGG_STD)
-          gvalid = __ldg(kp.gmask + bb * kp.gmB + q * kp.gmCam + d * kp.gmD + h * kp.gmY + w * kp.gmX) != 0;
-      }
-      make_entry(kp, gx, gy, off, lx, ly);
-      off += q * kp.fsCam;
-      if (AGG == MVSGI_AGG_STD && gvalid) info = make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch);
-    }
-    if (AGG == MVSGI_AGG_STD) {
-      const uint32_t* mb = kp.mbits + (kp.perFrameMasks ? (long long)b * kp.mbB : 0) + q * kp.mbCam;
-      bit = mask_eval(mask_fetch(mb, info, kp.mPitch), info);  // spherical_sweep_avg.py:92-102
-    } else {
-      bit = 1u;
-    }
-  }
-  int offs[CAM];
-  float lxs[CAM], lys[CAM];
-  uint32_t v = 0;
-#pragma unroll
-  for (int cam = 0; cam < CAM; ++cam) {
-    const int src = (lane & ~3) + cam;
-    offs[cam] = __shfl_sync(0xFFFFFFFFu, off, src);
-    lxs[cam] = __shfl_sync(0xFFFFFFFFu, lx, src);
-    lys[cam] = __shfl_sync(0xFFFFFFFFu, ly, src);
-    v |= __shfl_sync(0xFFFFFFFFu, bit, src) << cam;
-  }
-  (void)qmask;
-  const int n = __popc(v);
-  const bool need = act && (AGG == MVSGI_AGG_CONCAT || n > 1);  // :106-111, :125
-  if (!need) return;
-
-  const int cs = kp.Dvol * HW;
-  const int cLane = q * 4;
-  const float* fb = kp.feat + (long long)b * kp.fsB + cLane;
-  float* gb = kb.gradStage + (long long)b * kp.fsB + cLane;
-  const float* gv = kb.gradVol + ((long long)b * kp.Cout + cLane) * cs + (long long)(d + kp.dOff) * HW + pix;
-  const float inv = 1.0f / (float)n;
-
-  for (int cg = 0; cg < kp.CG; ++cg) {
-    const int nst = min(4, kp.C - (cg * kCG + cLane));  // staged channels >= C are padding
-    if (nst <= 0) continue;
-    float g[CAM][4];
-    if (AGG == MVSGI_AGG_STD) {
-      float f[CAM][4];
-#pragma unroll
-      for (int cam = 0; cam < CAM; ++cam) {
-        if ((v >> cam) & 1u) {
-          const float* t = fb + (long long)cg * kp.fsCg + offs[cam];
-          const float4 ta = ldg4(t), tc = ldg4(t + kCG), tb = ldg4(t + kp.fsY), td = ldg4(t + kp.fsY + kCG);
-          const float hx = 1.0f - lxs[cam], hy = 1.0f - lys[cam];
-          const float wa = hx * hy, wb = hx * lys[cam], wc = lxs[cam] * hy, wd = lxs[cam] * lys[cam];
-          f[cam][0] = fmaf(td.x, wd, fmaf(tc.x, wc, fmaf(tb.x, wb, ta.x * wa)));
-          f[cam][1] = fmaf(td.y, wd, fmaf(tc.y, wc, fmaf(tb.y, wb, ta.y * wa)));
-          f[cam][2] = fmaf(td.z, wd, fmaf(tc.z, wc, fmaf(tb.z, wb, ta.z * wa)));
-          f[cam][3] = fmaf(td.w, wd, fmaf(tc.w, wc, fmaf(tb.w, wb, ta.w * wa)));
-        } else {
-          f[cam][0] = f[cam][1] = f[cam][2] = f[cam][3] = 0.f;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float s = f[0][i];
-#pragma unroll
-        for (int cam = 1; cam < CAM; ++cam) s += f[cam][i];
-        const float avg = s * inv;
-        const float go = i < nst ? __ldg(gv + ((long long)cg * kCG + i) * cs) : 0.f;
-        const float k2 = 2.0f * go * inv;
-#pragma unroll
-        for (int cam = 0; cam < CAM; ++cam) g[cam][i] = (f[cam][i] - avg) * k2;
-      }
-    } else {
-#pragma unroll
-      for (int cam = 0; cam < CAM; ++cam)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          g[cam][i] = i < nst ? __ldg(gv + ((long long)cam * kp.C + cg * kCG + i) * cs) : 0.f;
-    }
-#pragma unroll
-    for (int cam = 0; cam < CAM; ++cam) {
-      if (!((v >> cam) & 1u)) continue;
-      if (offs[cam] == kp.zeroOff + cam * kp.fsCam) continue;  // sample entirely outside: nothing to accumulate
-      float* t = gb + (long long)cg * kp.fsCg + offs[cam];
-      const float hx = 1.0f - lxs[cam], hy = 1.0f - lys[cam];
-      const float wa = hx * hy, wb = hx * lys[cam], wc = lxs[cam] * hy, wd = lxs[cam] * lys[cam];
-      red_add4(t, g[cam][0] * wa, g[cam][1] * wa, g[cam][2] * wa, g[cam][3] * wa);
-      red_add4(t + kCG, g[cam][0] * wc, g[cam][1] * wc, g[cam][2] * wc, g[cam][3] * wc);
-      red_add4(t + kp.fsY, g[cam][0] * wb, g[cam][1] * wb, g[cam][2] * wb, g[cam][3] * wb);
-      red_add4(t + kp.fsY + kCG, g[cam][0] * wd, g[cam][1] * wd, g[cam][2] * wd, g[cam][3] * wd);
-    }
-  }
-}
+// red_add4: sweep.cuh
 
 // gradient image in staged layout -> grad_feats [B, CAM, C, Hf, Wf] (any element strides): the inverse of
 // stage_feats_kernel.  One block = one image row of one (b, cam, channel group).

@@ -535,37 +535,24 @@ int backward_plan(const MvsgiSweepBwdArgs* a, MvsgiSweepArgs* f, SweepPlan* p) {
   f->vol = const_cast<float*>(a->grad_vol);  // only has to be non-NULL for validation; never written
   f->valid_out = nullptr;
   f->num_peers = 0;
-  // the backward only uses the staging part of the plan: no geometry table in its workspace, features always staged
-  // (the gradient image it scatters into has the staged layout)
+  f->octet_order = nullptr;
+  f->order_runs = f->order_units = 0;
+  f->cta_times_out = nullptr;
+  // Channels-last features tapped in place (the forward's own rule) when the gradient has the same dense layout: the
+  // scatter then goes straight into grad_feats.  Otherwise features are staged and the gradient image has the staged
+  // layout (un-staged into grad_feats afterwards).
+  f->flags = MVSGI_FLAG_CTA_TABLE;
+  int rc = validate_and_plan(f, p);
+  if (rc != MVSGI_OK) return rc;
+  bool same = p->direct;
+  const int64_t* fs = f->feats_stride;
+  for (int i = 0; i < 5 && same; ++i) same = a->grad_feats_stride[i] == fs[i];
+  // dense: the frames tile memory without gaps, so one memset clears the gradient
+  same = same && fs[4] == f->feat_chs && fs[3] == fs[4] * f->feat_w && fs[1] == fs[3] * f->feat_h &&
+         fs[0] == fs[1] * f->num_cams && (reinterpret_cast<uintptr_t>(a->grad_feats) & 15) == 0;
+  if (same) return MVSGI_OK;
   f->flags = MVSGI_FLAG_CTA_TABLE | MVSGI_FLAG_STAGED_FEATS;
   return validate_and_plan(f, p);
-}
-
-template <int AGG>
-cudaError_t launch_backward_geom(int cams, const mvsgi::SweepKP& kp, const MvsgiRig& rig, uint4* out, cudaStream_t st) {
-  dim3 grid((kp.P + 127) / 128, kp.D);
-  switch (cams) {
-    case 1: mvsgi::sweep_backward_geom_kernel<1, AGG><<<grid, 128, 0, st>>>(kp, rig, out); break;
-    case 2: mvsgi::sweep_backward_geom_kernel<2, AGG><<<grid, 128, 0, st>>>(kp, rig, out); break;
-    case 3: mvsgi::sweep_backward_geom_kernel<3, AGG><<<grid, 128, 0, st>>>(kp, rig, out); break;
-    default: mvsgi::sweep_backward_geom_kernel<4, AGG><<<grid, 128, 0, st>>>(kp, rig, out); break;
-  }
-  g_launches++;
-  return cudaGetLastError();
-}
-
-template <int AGG>
-cudaError_t launch_sweep_backward(int cams, const mvsgi::SweepBwdKP& kb, const MvsgiRig& rig, cudaStream_t st) {
-  const int P = kb.f.P;
-  dim3 grid((P + mvsgi::kBwdThreads / 4 - 1) / (mvsgi::kBwdThreads / 4), kb.f.D, kb.f.B);
-  switch (cams) {
-    case 1: mvsgi::sweep_backward_kernel<1, AGG><<<grid, mvsgi::kBwdThreads, 0, st>>>(kb, rig); break;
-    case 2: mvsgi::sweep_backward_kernel<2, AGG><<<grid, mvsgi::kBwdThreads, 0, st>>>(kb, rig); break;
-    case 3: mvsgi::sweep_backward_kernel<3, AGG><<<grid, mvsgi::kBwdThreads, 0, st>>>(kb, rig); break;
-    default: mvsgi::sweep_backward_kernel<4, AGG><<<grid, mvsgi::kBwdThreads, 0, st>>>(kb, rig); break;
-  }
-  g_launches++;
-  return cudaGetLastError();
 }
 
 }  // namespace
@@ -834,17 +821,12 @@ int mvsgi_resample_f32(const MvsgiResampleArgs* a, void* stream) {
 
 // ---- backward passes -------------------------------------------------------------------------------------------------
 
-// geometry table of the backward (backward.cuh): only when the geometry is shared by the frames
-static int64_t backward_geom_bytes(const MvsgiSweepArgs& f, const SweepPlan& p) {
-  if (p.per_frame_grids) return 0;
-  return align_up((int64_t)f.num_cands * f.out_h * f.out_w * f.num_cams * 16, 256);
-}
-
 int64_t mvsgi_sweep_backward_workspace_bytes(const MvsgiSweepBwdArgs* a) {
   MvsgiSweepArgs f;
   SweepPlan p;
   const int rc = backward_plan(a, &f, &p);
-  return rc != MVSGI_OK ? (int64_t)rc : p.total_bytes + p.feats_bytes + backward_geom_bytes(f, p);
+  if (rc != MVSGI_OK) return (int64_t)rc;
+  return p.direct ? p.total_bytes : p.total_bytes + p.feats_bytes;
 }
 
 int mvsgi_sweep_backward_f32(const MvsgiSweepBwdArgs* a, void* stream) {
@@ -853,13 +835,37 @@ int mvsgi_sweep_backward_f32(const MvsgiSweepBwdArgs* a, void* stream) {
   int rc = backward_plan(a, &f, &p);
   if (rc != MVSGI_OK) return rc;
   if (a->workspace == nullptr) return MVSGI_E_NULL;
-  const int64_t geom_bytes = backward_geom_bytes(f, p);
-  if (a->workspace_bytes < p.total_bytes + p.feats_bytes + geom_bytes ||
+  if (p.tiled || p.walk) return MVSGI_E_UNSUPPORTED;  // experiment plans have no backward
+  if (a->workspace_bytes < p.total_bytes + (p.direct ? 0 : p.feats_bytes) ||
       (reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0)
     return MVSGI_E_WORKSPACE;
   if (f.batch > 65535 || f.num_cands > 65535 || f.feat_h > 65535) return MVSGI_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)a->workspace;
+  if (p.direct) {
+    // channels-last features and gradient: pack the masks (if they are not packed already), clear grad_feats, and run
+    // the backward instantiation of the sweep kernel on the caller's tensors — no staged copies
+    f.workspace = ws;
+    f.workspace_bytes = p.total_bytes;
+    f.flags |= MVSGI_FLAG_STAGE_ONLY;
+    rc = mvsgi_sweep_f32(&f, stream);
+    if (rc != MVSGI_OK) return rc;
+    const size_t gbytes = (size_t)f.batch * f.feats_stride[0] * sizeof(float);
+    cudaError_t e = cudaMemsetAsync(a->grad_feats, 0, gbytes, st);
+    if (e != cudaSuccess) return (int)e;
+    mvsgi::SweepKP kp;
+    fill_kp(&f, p, (float*)ws, (uint32_t*)(ws + p.feats_bytes), kp);
+    kp.vol = const_cast<float*>(a->grad_vol);
+    kp.volChannelsLast = 0;
+    kp.gradFeat = a->grad_feats;
+    kp.framesPerPass = 1;
+    MvsgiRig rig;
+    if (f.grid_mode == MVSGI_GRID_PROJECT) rig = *f.rig;
+    else memset(&rig, 0, sizeof(rig));
+    e = mvsgi::launch_sweep_bwd(f.aggregate, f.num_cams, kp, rig, p.grid, p.smem_bytes, st);
+    g_launches++;
+    return (int)e;
+  }
   // 1. stage feats + pack masks exactly as the forward does
   f.workspace = ws;
   f.workspace_bytes = p.total_bytes;
@@ -870,24 +876,18 @@ int mvsgi_sweep_backward_f32(const MvsgiSweepBwdArgs* a, void* stream) {
   float* gstage = (float*)(ws + p.total_bytes);
   cudaError_t e = cudaMemsetAsync(gstage, 0, (size_t)p.feats_bytes, st);
   if (e != cudaSuccess) return (int)e;
-  // 3. scatter
-  mvsgi::SweepBwdKP kb;
-  fill_kp(&f, p, (float*)ws, (uint32_t*)(ws + p.feats_bytes), kb.f);
-  kb.gradVol = a->grad_vol;
-  kb.gradStage = gstage;
-  kb.geom = nullptr;
+  // 3. scatter: the backward instantiation of the sweep kernel (sweep.cuh, BWD) on the staged copies
+  mvsgi::SweepKP kp;
+  fill_kp(&f, p, (float*)ws, (uint32_t*)(ws + p.feats_bytes), kp);
+  kp.vol = const_cast<float*>(a->grad_vol);
+  kp.volChannelsLast = 0;
+  kp.gradFeat = gstage;
+  kp.framesPerPass = 1;
   MvsgiRig rig;
   if (f.grid_mode == MVSGI_GRID_PROJECT) rig = *f.rig;
   else memset(&rig, 0, sizeof(rig));
-  if (geom_bytes > 0) {  // geometry once for all frames
-    uint4* geom = (uint4*)(ws + p.total_bytes + p.feats_bytes);
-    e = f.aggregate == MVSGI_AGG_STD ? launch_backward_geom<MVSGI_AGG_STD>(f.num_cams, kb.f, rig, geom, st)
-                                     : launch_backward_geom<MVSGI_AGG_CONCAT>(f.num_cams, kb.f, rig, geom, st);
-    if (e != cudaSuccess) return (int)e;
-    kb.geom = geom;
-  }
-  e = f.aggregate == MVSGI_AGG_STD ? launch_sweep_backward<MVSGI_AGG_STD>(f.num_cams, kb, rig, st)
-                                   : launch_sweep_backward<MVSGI_AGG_CONCAT>(f.num_cams, kb, rig, st);
+  e = mvsgi::launch_sweep_bwd(f.aggregate, f.num_cams, kp, rig, p.grid, p.smem_bytes, st);
+  g_launches++;
   if (e != cudaSuccess) return (int)e;
   // 4. staged gradient -> grad_feats
   const int N = f.batch * f.num_cams;

@@ -66,6 +66,9 @@ struct SweepKP {
   const int* octOrder;
   int octUnits;
   unsigned long long* ctaTimes;  // optional [gridDim.x][4] (MvsgiSweepArgs.cta_times_out)
+  // backward instantiation (BWD): `vol` is the upstream gradient of the volume (read), gradFeat the zero-initialised
+  // gradient image with the element layout of `feat` that the sampler's adjoint accumulates into
+  float* gradFeat;
   int wL, wSegs, wNumSeg;  // sweep_walk.cuh: segment length, segments per run, segments in the image
   // staged features: element (b, cam, cg, yp, xp, c) at feat[b*fsB + cam*fsCam + cg*fsCg + yp*fsY + xp*16 + c]
   const float* feat;
@@ -272,11 +275,23 @@ MVSGI_DEV unsigned long long gtimer() {
   return t;
 }
 
+MVSGI_DEV void red_add4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// BWD = true: the backward pass on the same work decomposition (table build, mask lookups, frame loop) — per voxel the
+// forward samples are re-gathered, d vol / d f_k = (2 / n)(f_k - mean) * grad_vol (std) or grad_vol itself (concat) is
+// formed in registers and scattered to the four taps of every sampled camera with red.global.add.v4.f32
+// (backports.py:76-86 backward; spherical_sweep_avg.py:114-125).  384 threads x 2 CTAs (85 registers), one frame per pass.
+constexpr int kSweepBwdThreads = 384;
+__host__ __device__ constexpr int sweep_nt(int fb, bool bwd) { return bwd ? kSweepBwdThreads : sweep_threads(fb); }
+
 template <int CAM, int AGG, bool FULLC, bool VALID, bool PEERS, bool CL, bool BF16, bool DIRECT = false, bool VBF16 = false,
-          int FB = 1>
-__global__ void __launch_bounds__(sweep_threads(FB), sweep_ctas(FB))
+          int FB = 1, bool BWD = false>
+__global__ void __launch_bounds__(sweep_nt(FB, BWD), BWD ? 2 : sweep_ctas(FB))
 sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
-  constexpr int NT = sweep_threads(FB);
+  constexpr int NT = sweep_nt(FB, BWD);
+  static_assert(!BWD || (FB == 1 && !VALID && !PEERS && !BF16 && !VBF16), "backward: one fp32 frame per pass");
   // MvsgiSweepArgs.cta_times_out: (SM id, start, end of the first table build, end) of every CTA in globaltimer
   // nanoseconds — what ops.calibrated_octet_order() reads to find the SMs that run this kernel slower than the rest
   if (kp.ctaTimes != nullptr && threadIdx.x == 0) {
@@ -445,6 +460,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       typedef typename VolT<VBF16>::type VT;  // element type of the volume (same element offsets)
       const long long volB = (long long)kp.Cout * cs;
       VT* vq = reinterpret_cast<VT*>(kp.vol) + (long long)b * volB + (CL ? (long long)cLane : (long long)cLane * cs);
+      float* gbq = BWD ? kp.gradFeat + (long long)b * kp.fsB + cLane : nullptr;
       int fsY = kp.fsY, zeroOff = kp.zeroOff, csr = cs, fX = kp.fX;
       asm volatile("" : "+l"(fbq), "+l"(vq), "+r"(fsY), "+r"(zeroOff), "+r"(csr), "+r"(fX));
       long long fsB = kp.fsB;  // frames of a pass are fsB elements apart
@@ -463,7 +479,94 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         const FT* fcg = fbq;
         VT* vcg = vq + (CL ? (long long)po * kp.Cout : (long long)po);
 
+        // backward only: tap offsets (relative to the lane's pointer into the (frame, channel group) image) and bilinear
+        // weights of camera `cam` for this voxel, exactly as the forward loop below derives them
+        auto decode = [&](int cam, bool ld, int& o00, int& o01, int& o10, int& o11, float& wa, float& wb, float& wc,
+                          float& wd) {
+          const int offr = (int)rec[2 + 3 * cam];
+          const int off = DIRECT ? (offr & ~15) : (ld ? offr : zeroOff);
+          const float lx = __uint_as_float(rec[3 + 3 * cam]);
+          float ly = __uint_as_float(rec[4 + 3 * cam]);
+          float hx = ld ? 1.0f - lx : 0.0f, hy = 1.0f - ly;
+          float lxe = ld ? lx : 0.0f;
+          int dx = kCG, dy = fsY;
+          if (DIRECT && ((offr & 15) != 0 || fX != kCG)) {
+            const int xm = offr & 3, ym = (offr >> 2) & 3;
+            if (xm == 1) hx = 0.0f;
+            if (xm == 2) lxe = 0.0f;
+            if (ym == 1) hy = 0.0f;
+            if (ym == 2) ly = 0.0f;
+            if (ym) dy = 0;
+            dx = xm ? 0 : fX;
+          }
+          o00 = off; o01 = off + dx; o10 = off + dy; o11 = off + dy + dx;
+          wa = __fmul_rn(hx, hy); wb = __fmul_rn(hx, ly); wc = __fmul_rn(lxe, hy); wd = __fmul_rn(lxe, ly);
+        };
+
         for (int cg = 0; cg < kp.CG; ++cg, fcg += kp.fsCg, vcg += (CL ? (long long)kCG : kCG * (long long)csr)) {
+          if (BWD) {
+            const int nstb = FULLC ? 4 : kp.C - (cg * kCG + cLane);  // staged channels >= C are padding
+            const float* gvc = reinterpret_cast<const float*>(vcg);
+            float g[CAM][4];
+            if (AGG == MVSGI_AGG_STD) {
+              float fk[CAM][4];
+#pragma unroll
+              for (int cam = 0; cam < CAM; ++cam) {
+                const bool ld = need && ((v >> cam) & 1u);
+                fk[cam][0] = fk[cam][1] = fk[cam][2] = fk[cam][3] = 0.f;
+                if (__any_sync(0xFFFFFFFFu, ld)) {
+                  int o00, o01, o10, o11;
+                  float wa, wb, wc, wd;
+                  decode(cam, ld, o00, o01, o10, o11, wa, wb, wc, wd);
+                  const float4 ta = ldg4(fcg + o00), tc = ldg4(fcg + o01), tb = ldg4(fcg + o10), td = ldg4(fcg + o11);
+                  // the forward's sum: (column x0) + (column x1)
+                  fk[cam][0] = __fadd_rn(__fmaf_rn(tb.x, wb, __fmul_rn(ta.x, wa)), __fmaf_rn(td.x, wd, __fmul_rn(tc.x, wc)));
+                  fk[cam][1] = __fadd_rn(__fmaf_rn(tb.y, wb, __fmul_rn(ta.y, wa)), __fmaf_rn(td.y, wd, __fmul_rn(tc.y, wc)));
+                  fk[cam][2] = __fadd_rn(__fmaf_rn(tb.z, wb, __fmul_rn(ta.z, wa)), __fmaf_rn(td.z, wd, __fmul_rn(tc.z, wc)));
+                  fk[cam][3] = __fadd_rn(__fmaf_rn(tb.w, wb, __fmul_rn(ta.w, wa)), __fmaf_rn(td.w, wd, __fmul_rn(tc.w, wc)));
+                }
+              }
+              const float inv = n == 2 ? 0.5f : (n == 3 ? (1.0f / 3.0f) : 0.25f);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float go = 0.f;
+                if (need && i < nstb) go = CL ? __ldg(gvc + i) : __ldg(gvc + (long long)i * csr);
+                float sm = fk[0][i];
+#pragma unroll
+                for (int cam = 1; cam < CAM; ++cam) sm += fk[cam][i];
+                const float avg = sm * inv;
+                const float k2 = 2.0f * go * inv;  // :114-125: the term through the mean cancels
+#pragma unroll
+                for (int cam = 0; cam < CAM; ++cam) g[cam][i] = (fk[cam][i] - avg) * k2;
+              }
+            } else {  // concat: the gradient of channel cam * C + c of the volume
+#pragma unroll
+              for (int cam = 0; cam < CAM; ++cam)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const long long ch = (long long)cam * kp.C + i;
+                  g[cam][i] = (act && i < nstb) ? (CL ? __ldg(gvc + ch) : __ldg(gvc + ch * csr)) : 0.f;
+                }
+            }
+            float* gcg = gbq + (long long)cg * kp.fsCg;
+#pragma unroll
+            for (int cam = 0; cam < CAM; ++cam) {
+              const bool ld = need && ((v >> cam) & 1u);
+              if (__any_sync(0xFFFFFFFFu, ld)) {
+                int o00, o01, o10, o11;
+                float wa, wb, wc, wd;
+                decode(cam, ld, o00, o01, o10, o11, wa, wb, wc, wd);
+                // a sample whose taps all lie in the padding reads the all-zero patch: nothing to accumulate
+                if (ld && (DIRECT || (int)rec[2 + 3 * cam] != zeroOff + cam * kp.fsCam)) {
+                  red_add4(gcg + o00, g[cam][0] * wa, g[cam][1] * wa, g[cam][2] * wa, g[cam][3] * wa);
+                  red_add4(gcg + o01, g[cam][0] * wc, g[cam][1] * wc, g[cam][2] * wc, g[cam][3] * wc);
+                  red_add4(gcg + o10, g[cam][0] * wb, g[cam][1] * wb, g[cam][2] * wb, g[cam][3] * wb);
+                  red_add4(gcg + o11, g[cam][0] * wd, g[cam][1] * wd, g[cam][2] * wd, g[cam][3] * wd);
+                }
+              }
+            }
+            continue;
+          }
           f32x2 f[FB][CAM][2];  // this lane's 4 channels of every camera's sample, as two packed pairs
 #pragma unroll
           for (int cam = 0; cam < CAM; ++cam) {

@@ -465,7 +465,14 @@ def sweep_backward_op(grad_vol: Tensor, feats: Tensor, grids: Optional[Tensor], 
     if tuple(grad_vol.shape) != (B, cout, num_cands, out_h, out_w) or grad_vol.dtype != torch.float32:
         raise RuntimeError(f"grad_vol must be float32 [{B}, {cout}, {num_cands}, {out_h}, {out_w}]")
     grad_vol = grad_vol.contiguous()
-    grad_feats = torch.empty_like(feats, memory_format=torch.contiguous_format)
+    # dense channels-last features (element (b, cam, y, x, c) at unit channel stride): the gradient gets the same layout
+    # and the kernel scatters straight into it; anything else is staged and the gradient is NCHW
+    B_, CAM_, C_, Hf_, Wf_ = feats.shape
+    nhwc = (CAM_ * Hf_ * Wf_ * C_, Hf_ * Wf_ * C_, 1, Wf_ * C_, C_)
+    if tuple(feats.stride()) == nhwc and C_ % 16 == 0:
+        grad_feats = torch.empty_strided(feats.shape, nhwc, dtype=torch.float32, device=feats.device)
+    else:
+        grad_feats = torch.empty_like(feats, memory_format=torch.contiguous_format)
     b = abi.MvsgiSweepBwdArgs()
     b.struct_size = C.sizeof(abi.MvsgiSweepBwdArgs)
     b.fwd = C.pointer(fwd.args)
@@ -484,6 +491,10 @@ def sweep_backward_op(grad_vol: Tensor, feats: Tensor, grids: Optional[Tensor], 
 
 @sweep_backward_op.register_fake
 def _(grad_vol, feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, mask_h=0, mask_w=0):
+    B_, CAM_, C_, Hf_, Wf_ = feats.shape
+    nhwc = (CAM_ * Hf_ * Wf_ * C_, Hf_ * Wf_ * C_, 1, Wf_ * C_, C_)
+    if tuple(feats.stride()) == nhwc and C_ % 16 == 0:
+        return torch.empty_strided(feats.shape, nhwc, dtype=torch.float32, device=feats.device)
     return torch.empty_like(feats, memory_format=torch.contiguous_format)
 
 

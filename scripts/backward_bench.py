@@ -61,9 +61,26 @@ def fwd_bwd(i):  # through autograd, the way training_step calls it
     vol.backward(gv)
 
 
+def nhwc(f):
+    return f.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+
+
+sets_cl = [nhwc(f.detach()) for f, _, _ in sets]
+
+
+def sweep_bwd_cl(i):  # channels-last features: the gradient is scattered straight into a channels-last grad_feats
+    return ops.sweep_backward_op(sets[i % 3][1], sets_cl[i % 3], None, None, masks, blob, abi.AGG_STD, w.cv_hw[0],
+                                 w.cv_hw[1], w.num_cands)
+
+
 l0 = ops.launch_counter()
 ms_sweep = timed(sweep_bwd)
 launches = (ops.launch_counter() - l0) / 18
+l0 = ops.launch_counter()
+ms_sweep_cl = timed(sweep_bwd_cl)
+launches_cl = (ops.launch_counter() - l0) / 18
+g_a, g_b = sweep_bwd(0), sweep_bwd_cl(0)
+rel_cl = float((g_a - g_b).abs().max() / g_a.abs().max())
 ms_soft = timed(soft_bwd)
 ms_fb = timed(fwd_bwd)
 peak = 6544.0
@@ -79,6 +96,9 @@ print(json.dumps({
     "workload": "G16V", "frames": B, "sweep_backward_ms": ms_sweep, "sweep_backward_launches": launches,
     "sweep_backward_algorithmic_gbs": sweep_bytes / (ms_sweep * 1e-3) / 1e9,
     "sweep_backward_frac_of_peak": sweep_bytes / (ms_sweep * 1e-3) / 1e9 / peak,
+    "sweep_backward_channels_last_ms": ms_sweep_cl, "sweep_backward_channels_last_launches": launches_cl,
+    "sweep_backward_channels_last_frac_of_peak": B * (w.vol_bytes() + 3 * w.feats_bytes()) / (ms_sweep_cl * 1e-3) / 1e9 / peak,
+    "channels_last_vs_nchw_rel_diff": rel_cl,
     "softargmin_backward_ms": ms_soft, "softargmin_backward_algorithmic_gbs": soft_bytes / (ms_soft * 1e-3) / 1e9,
     "softargmin_backward_frac_of_peak": soft_bytes / (ms_soft * 1e-3) / 1e9 / peak,
     "sweep_forward_plus_backward_autograd_ms": ms_fb, "peak_gbs": peak}))
