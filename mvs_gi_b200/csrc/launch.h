@@ -31,7 +31,7 @@ cudaError_t launch_sweep_cta(int aggregate, int cams, const SweepKP& kp, const M
 // sweep_cta_fb.cu: the same kernel with several frames per pass (kp.framesPerPass > 1)
 cudaError_t launch_sweep_cta_fb(int aggregate, int cams, const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
                                 cudaStream_t st);
-// sweep_bwd.cu: the backward instantiation of the same kernel (sweep.cuh, BWD): scatter into kp.gradFeat
+// sweep_bwd_std.cu / sweep_bwd_concat.cu: the backward instantiation of the same kernel (sweep.cuh, BWD): scatter into kp.gradFeat
 cudaError_t launch_sweep_bwd(int aggregate, int cams, const SweepKP& kp, const MvsgiRig& rig, int grid, size_t smem,
                              cudaStream_t st);
 // softargmin_tma.cu: scale-factor-2 soft-argmin with the input box staged by TMA; false = not applicable, nothing launched
