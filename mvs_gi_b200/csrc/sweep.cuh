@@ -366,46 +366,62 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
     __syncthreads();
 
     // ---------------------------------------------------------------- build: geometry -> tap table
+    // one table entry: camera `cam` of pair j = (candidate d0 + dd, pixel slot p of the run)
+    auto build_entry = [&](int b, int cam, int j, int dd, int p) {
+      const int d = d0 + dd;
+      const int pixr = pixel_of(p);
+      const int pix = min(pixr, kp.P - 1);  // only the last octet of the image can be ragged
+      float gx, gy;
+      bool gvalid = true;
+      if (kp.gridMode == MVSGI_GRID_PROJECT) {
+        float x, y, z;
+        to_camera(rig.cams[cam], rays[3 * p], rays[3 * p + 1], rays[3 * p + 2], rig.dist[d], x, y, z);
+        gvalid = project(rig.cams[cam], x, y, z, gx, gy);
+      } else {
+        const int h = pix / kp.Wo, w = pix - h * kp.Wo;
+        const long long go = (long long)b * kp.gsB + cam * kp.gsCam + d * kp.gsD + h * kp.gsY + w * kp.gsX;
+        const float2 g = __ldg(reinterpret_cast<const float2*>(kp.grids + go));
+        gx = g.x;
+        gy = g.y;
+        if (AGG == MVSGI_AGG_STD)
+          gvalid = __ldg(kp.gmask + (long long)b * kp.gmB + cam * kp.gmCam + d * kp.gmD + h * kp.gmY + w * kp.gmX) != 0;
+      }
+      int off;
+      float lx, ly;
+      if (DIRECT) make_entry_direct(kp, gx, gy, off, lx, ly);
+      else make_entry(kp, gx, gy, off, lx, ly);
+      uint32_t* rec = tab + (size_t)j * ES;
+      rec[2 + 3 * cam] = (uint32_t)(off + cam * kp.fsCam);
+      rec[3 + 3 * cam] = __float_as_uint(lx);
+      rec[4 + 3 * cam] = __float_as_uint(ly);
+      if (AGG == MVSGI_AGG_STD)
+        tMi[cam * MP + j] = gvalid ? make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch) : kMaskNone;
+      if (cam == 0) {
+        rec[0] = pixr < kp.P ? (uint32_t)((d + kp.dOff) * HW + pix) : 0xFFFFFFFFu;  // negative: nothing to store
+        if (AGG == MVSGI_AGG_CONCAT) rec[1] = ((1u << CAM) - 1u) * 0x0101u;
+      }
+    };
     auto build = [&](int b) {
+      if (ngroups == 1) {
+        // one locality group (the default plan): pair j = dd * npx + p.  Cameras outermost with a compile-time index
+        // (the camera's parameters are then constant-bank operands), the candidate by a multiply-high instead of a
+        // division: j < 2^16 and npx < 2^16, so floor(j * ceil(2^32 / npx) / 2^32) = j / npx exactly.
+        const uint32_t magic = 0xFFFFFFFFu / (uint32_t)npx + 1u;
+#pragma unroll
+        for (int cam = 0; cam < CAM; ++cam)
+          for (int j = tid; j < npairs; j += NT) {
+            const int dd = (int)__umulhi((uint32_t)j, magic);
+            build_entry(b, cam, j, dd, j - dd * npx);
+          }
+        return;
+      }
       for (int e = tid; e < CAM * npairs; e += NT) {
         const int cam = e / npairs, j = e - cam * npairs;
         const int gi = j / (gsz * dcount);
         const int local = j - gi * gsz * dcount;
         const int gcount = min(gsz, npx - gi * gsz);
         const int dd = local / gcount;
-        const int p = gi * gsz + (local - dd * gcount);
-        const int d = d0 + dd;
-        const int pixr = pixel_of(p);
-        const int pix = min(pixr, kp.P - 1);  // only the last octet of the image can be ragged
-        const int h = pix / kp.Wo, w = pix - h * kp.Wo;
-        float gx, gy;
-        bool gvalid = true;
-        if (kp.gridMode == MVSGI_GRID_PROJECT) {
-          float x, y, z;
-          to_camera(rig.cams[cam], rays[3 * p], rays[3 * p + 1], rays[3 * p + 2], rig.dist[d], x, y, z);
-          gvalid = project(rig.cams[cam], x, y, z, gx, gy);
-        } else {
-          const long long go = (long long)b * kp.gsB + cam * kp.gsCam + d * kp.gsD + h * kp.gsY + w * kp.gsX;
-          const float2 g = __ldg(reinterpret_cast<const float2*>(kp.grids + go));
-          gx = g.x;
-          gy = g.y;
-          if (AGG == MVSGI_AGG_STD)
-            gvalid = __ldg(kp.gmask + (long long)b * kp.gmB + cam * kp.gmCam + d * kp.gmD + h * kp.gmY + w * kp.gmX) != 0;
-        }
-        int off;
-        float lx, ly;
-        if (DIRECT) make_entry_direct(kp, gx, gy, off, lx, ly);
-        else make_entry(kp, gx, gy, off, lx, ly);
-        uint32_t* rec = tab + (size_t)j * ES;
-        rec[2 + 3 * cam] = (uint32_t)(off + cam * kp.fsCam);
-        rec[3 + 3 * cam] = __float_as_uint(lx);
-        rec[4 + 3 * cam] = __float_as_uint(ly);
-        if (AGG == MVSGI_AGG_STD)
-          tMi[cam * MP + j] = gvalid ? make_mask_info(gx, gy, kp.Hm, kp.Wm, kp.mPitch) : kMaskNone;
-        if (cam == 0) {
-          rec[0] = pixr < kp.P ? (uint32_t)((d + kp.dOff) * HW + pix) : 0xFFFFFFFFu;  // negative: nothing to store
-          if (AGG == MVSGI_AGG_CONCAT) rec[1] = ((1u << CAM) - 1u) * 0x0101u;
-        }
+        build_entry(b, cam, j, dd, gi * gsz + (local - dd * gcount));
       }
     };
     // Validity bits of every pair for frame b: consecutive threads = consecutive pixels of one camera and candidate,
@@ -424,14 +440,14 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
 #pragma unroll
         for (int cam = 0; cam < CAM; ++cam) v |= mask_eval(m[cam], info[cam]) << cam;
         vb8[(size_t)j * ES * 4] = (unsigned char)v;
+        if (!kp.perFrameMasks) vb8[(size_t)j * ES * 4 + 1 - 2 * (b & 1)] = (unsigned char)v;  // shared masks: both parities
       }
     };
     if (!kp.perFrameGrids) {
       build(0);
       __syncthreads();
-      if (AGG == MVSGI_AGG_STD) {  // frame 0 (and, when masks are shared, every frame: both parities)
+      if (AGG == MVSGI_AGG_STD) {  // frame 0 (and, when masks are shared, every frame: both parity bytes at once)
         lookup_masks(0);
-        if (!kp.perFrameMasks) lookup_masks(1);
         __syncthreads();
       }
     }
