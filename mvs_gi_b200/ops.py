@@ -344,7 +344,7 @@ def cta_times(call: "SweepCall", launches: int = 3):
     return sm, np.stack(out)
 
 
-def calibrated_octet_order(call: "SweepCall", rounds: int = 3, threshold: float = 0.015):
+def calibrated_octet_order(call: "SweepCall", rounds: int = 3, threshold: float = 0.015, launches: int = 3):
     """balanced_octet_order(), then a few measured corrections: the sweep is run with the table and per-CTA timestamps
     (MvsgiSweepArgs.cta_times_out); a CTA that finishes later than the median — on the B200s measured the same handful
     of CTA slots does, launch after launch, by 5-8 %: the placement of a full one-wave grid on the SMs repeats — gets
@@ -367,7 +367,7 @@ def calibrated_octet_order(call: "SweepCall", rounds: int = 3, threshold: float 
                       "mvsgi_sweep_octet_cost")
         cost = cost_t.cpu().numpy()
         call.set_octet_order(order)
-        _, us = cta_times(call)
+        _, us = cta_times(call, launches)
         ctas = us.shape[1]
         best, best_us = order, float(us.max(axis=1).min())
         report = {"calibrated": False, "kernel_us_balanced": best_us, "kernel_us_rounds": []}
@@ -382,7 +382,7 @@ def calibrated_octet_order(call: "SweepCall", rounds: int = 3, threshold: float 
             slow = slow / np.median(slow)
             cand = torch.from_numpy(deal_octets(cost, runs, units, ctas, slow)).to(call.device)
             call.set_octet_order(cand)
-            _, us = cta_times(call)
+            _, us = cta_times(call, launches)
             k_us = float(us.max(axis=1).min())
             report["kernel_us_rounds"].append(k_us)
             if k_us < best_us:

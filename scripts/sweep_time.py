@@ -31,7 +31,9 @@ calls = [ops.SweepCall(f, None, None, masks if agg == abi.AGG_STD else None, rig
 balanced = False
 if os.environ.get("BALANCE", "1") != "0":  # cost-balanced runs (ops.balanced_octet_order), computed once
     if os.environ.get("BALANCE") == "2":  # + measured correction
-        order, rep = ops.calibrated_octet_order(calls[0])
+        order, rep = ops.calibrated_octet_order(calls[0], rounds=int(os.environ.get("CAL_ROUNDS", "3")),
+                                                launches=int(os.environ.get("CAL_LAUNCHES", "3")),
+                                                threshold=float(os.environ.get("CAL_THRESHOLD", "0.015")))
         print("calibration:", json.dumps(rep), flush=True)
     else:
         order = ops.balanced_octet_order(calls[0])
