@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MVSGI_ABI_VERSION 12
+#define MVSGI_ABI_VERSION 13
 #define MVSGI_MAX_CAMS 4
 #define MVSGI_MAX_CANDS 64
 #define MVSGI_MAX_PEERS 7 /* extra destinations of a candidate-sharded sweep (8 GPUs of one box) */
@@ -208,7 +208,33 @@ typedef struct MvsgiSweepArgs {
    * runs — and which SMs: the CTA-to-SM placement of a full one-wave grid repeats from launch to launch — finish late;
    * ops.calibrated_octet_order() re-deals the octets with them.  NULL = not recorded (no cost). */
   uint64_t* cta_times_out;
+
+  /* Tap table kept across calls (optional; static calibration and static masks — the inference configuration).  The
+   * sweep kernel turns the rig's geometry into a shared-memory table of (output offset, validity bits, per camera: tap
+   * offset and the two bilinear fractions) records before it sweeps the frames; that table depends only on the rig, the
+   * masks, the shapes / strides of feats and vol and the work assignment — not on the features — so it plays the role
+   * of the grids the reference's dataset precomputes once per rig (multi_view_camera_model_dataset.py:519-557) and hands
+   * to every forward (spherical_sweep_avg.py:138-167).  tap_table is a DEVICE buffer of mvsgi_sweep_tap_table_bytes(args)
+   * bytes, 256-byte aligned:
+   *   MVSGI_TAP_TABLE_BUILD  the kernel builds its tables as usual and also stores them to tap_table;
+   *   MVSGI_TAP_TABLE_USE    the kernel copies each work item's table from tap_table into shared memory with one bulk
+   *                          asynchronous copy (cp.async.bulk + mbarrier) instead of evaluating the geometry.
+   * A table is valid for calls whose arguments equal the BUILD call's except feats / vol / workspace pointer VALUES
+   * (same strides, masks contents, rig, octet_order contents, batch); the volume is bit-identical to MVSGI_TAP_TABLE_OFF.
+   * Pays when the batch does not amortise the build: high-D (64 candidates, 160x640, 2 frames) 0.73 -> see DESIGN §6. */
+  void* tap_table;
+  int64_t tap_table_bytes;
+  int32_t tap_table_mode; /* MVSGI_TAP_TABLE_* */
+  int32_t reserved2;
 } MvsgiSweepArgs;
+
+#define MVSGI_TAP_TABLE_OFF 0
+#define MVSGI_TAP_TABLE_BUILD 1
+#define MVSGI_TAP_TABLE_USE 2
+
+/* Bytes of MvsgiSweepArgs.tap_table for this problem; 0 when the problem keeps no reusable table (per-frame grids or
+ * per-frame masks: the table changes with every frame); negative = error.  args->tap_table* are ignored. */
+int64_t mvsgi_sweep_tap_table_bytes(const MvsgiSweepArgs* args);
 
 /* Scratch the sweep needs for this problem (channels-last staging of feats when
  * they are not already channels-last — see MVSGI_FLAG_STAGED_FEATS —, bit-packed masks,

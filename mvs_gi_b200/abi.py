@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 MAX_CAMS = 4
 MAX_CANDS = 64
 MAX_PEERS = 7
@@ -20,6 +20,7 @@ CAM_EQUIRECT, CAM_DOUBLE_SPHERE, CAM_LINEAR_SPHERE = 0, 1, 2
 GRID_SUPPLIED, GRID_PROJECT = 0, 1
 AGG_STD, AGG_CONCAT = 0, 1
 MASK_F32, MASK_U8, MASK_PACKED = 0, 1, 2
+TAP_TABLE_OFF, TAP_TABLE_BUILD, TAP_TABLE_USE = 0, 1, 2
 FLAG_FEATS_BF16 = 1
 FLAG_STAGE_ONLY = 2
 FLAG_SWEEP_ONLY = 4
@@ -103,6 +104,10 @@ class MvsgiSweepArgs(C.Structure):
         ("order_runs", C.c_int32),
         ("order_units", C.c_int32),
         ("cta_times_out", C.c_void_p),
+        ("tap_table", C.c_void_p),
+        ("tap_table_bytes", C.c_int64),
+        ("tap_table_mode", C.c_int32),
+        ("reserved2", C.c_int32),
     ]
 
 
@@ -189,6 +194,7 @@ EXPORTS = {
                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mvsgi_sweep_octet_cost": (C.c_int, [C.POINTER(MvsgiSweepArgs), C.c_void_p, C.c_void_p]),
     "mvsgi_sweep_grid": (C.c_int, [C.POINTER(MvsgiSweepArgs)]),
+    "mvsgi_sweep_tap_table_bytes": (C.c_int64, [C.POINTER(MvsgiSweepArgs)]),
     "mvsgi_project_only_f32": (C.c_int, [C.POINTER(MvsgiProjectArgs), C.c_void_p]),
     "mvsgi_resample_f32": (C.c_int, [C.POINTER(MvsgiResampleArgs), C.c_void_p]),
     "mvsgi_mask_pitch_words": (C.c_int32, [C.c_int32]),

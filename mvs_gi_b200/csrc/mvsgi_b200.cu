@@ -127,6 +127,9 @@ struct SweepPlan {
   int tile_h, oct_per_row, tiles_x, num_tiles, steps_per_item, items_per_tile, tiled_items;
   int chunk_bytes, minfo_off, vinfo_off, tiled_grid;
   int64_t table_bytes;
+  // MvsgiSweepArgs.tap_table: words per item (a multiple of 4, so every item starts 16-byte aligned) and total bytes;
+  // 0 = this problem keeps no reusable table
+  int64_t tap_item_words, tap_bytes;
 };
 
 int mask_pitch_words(int mask_w) { return (mask_w + 31) / 32 + 2; }  // zero guard word + data words + zero guard
@@ -366,6 +369,21 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
   }
 #endif
 
+  // Tap table kept across calls (MvsgiSweepArgs.tap_table): one slot of max_pairs records per item
+  p->tap_item_words = 0;
+  p->tap_bytes = 0;
+  if (!p->per_frame_grids && !p->per_frame_masks && !p->tiled && !p->walk) {
+    p->tap_item_words = align_up((int64_t)p->max_pairs * mvsgi::entry_words(a->num_cams), 4);
+    p->tap_bytes = align_up((int64_t)p->num_items * p->tap_item_words * 4, 256);
+  }
+  if (a->tap_table_mode != MVSGI_TAP_TABLE_OFF) {
+    if (a->tap_table_mode != MVSGI_TAP_TABLE_BUILD && a->tap_table_mode != MVSGI_TAP_TABLE_USE) return MVSGI_E_UNSUPPORTED;
+    if (p->tap_bytes == 0) return MVSGI_E_UNSUPPORTED;
+    if (a->tap_table == nullptr) return MVSGI_E_NULL;
+    if (a->tap_table_bytes < p->tap_bytes || (reinterpret_cast<uintptr_t>(a->tap_table) & 255) != 0) return MVSGI_E_WORKSPACE;
+    if (p->tap_item_words * 4 >= (1ll << 20)) return MVSGI_E_SHAPE;  // one mbarrier transaction per item
+  }
+
   p->table_bytes = 0;
 #ifdef MVSGI_EXPERIMENTS
   if (p->tiled) {
@@ -415,6 +433,9 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   kp.octOrder = p.oct_order ? a->octet_order : nullptr;
   kp.octUnits = p.oct_order ? a->order_units : 0;
   kp.ctaTimes = reinterpret_cast<unsigned long long*>(a->cta_times_out);
+  kp.tapTable = a->tap_table_mode != MVSGI_TAP_TABLE_OFF ? reinterpret_cast<uint32_t*>(a->tap_table) : nullptr;
+  kp.tapItemWords = (int)p.tap_item_words;
+  kp.tapUse = a->tap_table_mode == MVSGI_TAP_TABLE_USE ? 1 : 0;
   kp.wL = p.walk ? p.w_len : 0; kp.wSegs = p.walk ? p.w_segs : 0; kp.wNumSeg = p.walk ? p.w_num_seg : 0;
   if (p.direct) {  // the caller's channels-last tensor: element (b, cam, y, x, c) at b*s0 + cam*s1 + y*s3 + x*s4 + c
     kp.feat = a->feats;
@@ -538,6 +559,7 @@ int backward_plan(const MvsgiSweepBwdArgs* a, MvsgiSweepArgs* f, SweepPlan* p) {
   f->octet_order = nullptr;
   f->order_runs = f->order_units = 0;
   f->cta_times_out = nullptr;
+  f->tap_table_mode = MVSGI_TAP_TABLE_OFF;  // the backward's plan is its own (one frame per pass, no balanced runs)
   // Channels-last features tapped in place (the forward's own rule) when the gradient has the same dense layout: the
   // scatter then goes straight into grad_feats.  Otherwise features are staged and the gradient image has the staged
   // layout (un-staged into grad_feats afterwards).
@@ -591,6 +613,7 @@ int mvsgi_sweep_balance_shape(const MvsgiSweepArgs* a, int32_t* runs_out, int32_
   MvsgiSweepArgs b = *a;
   b.octet_order = nullptr;
   b.order_runs = b.order_units = 0;
+  b.tap_table_mode = MVSGI_TAP_TABLE_OFF;
   if (b.vol == nullptr) b.vol = reinterpret_cast<float*>(static_cast<uintptr_t>(256));  // never written here: the problem may be described without outputs
   SweepPlan p;
   const int rc = validate_and_plan(&b, &p);
@@ -617,9 +640,23 @@ int mvsgi_sweep_grid(const MvsgiSweepArgs* a) {
   return p.tiled ? p.tiled_grid : p.grid;
 }
 
+int64_t mvsgi_sweep_tap_table_bytes(const MvsgiSweepArgs* a) {
+  if (a == nullptr) return MVSGI_E_NULL;
+  MvsgiSweepArgs b = *a;
+  b.tap_table = nullptr;
+  b.tap_table_bytes = 0;
+  b.tap_table_mode = MVSGI_TAP_TABLE_OFF;
+  if (b.vol == nullptr) b.vol = reinterpret_cast<float*>(static_cast<uintptr_t>(256));
+  SweepPlan p;
+  const int rc = validate_and_plan(&b, &p);
+  if (rc != MVSGI_OK) return rc;
+  return p.tap_bytes;
+}
+
 int mvsgi_sweep_octet_cost(const MvsgiSweepArgs* a, int32_t* cost_out, void* stream) {
   if (a == nullptr || cost_out == nullptr) return MVSGI_E_NULL;
   MvsgiSweepArgs b = *a;
+  b.tap_table_mode = MVSGI_TAP_TABLE_OFF;
   b.octet_order = nullptr;
   b.order_runs = b.order_units = 0;
   if (b.vol == nullptr) b.vol = reinterpret_cast<float*>(static_cast<uintptr_t>(256));  // never written here: the problem may be described without outputs

@@ -66,6 +66,10 @@ struct SweepKP {
   const int* octOrder;
   int octUnits;
   unsigned long long* ctaTimes;  // optional [gridDim.x][4] (MvsgiSweepArgs.cta_times_out)
+  // MvsgiSweepArgs.tap_table: item i's records at tapTable + i * tapItemWords (16-byte aligned); tapUse = 1: copied in
+  // instead of built, 0: built and stored; nullptr = not kept
+  uint32_t* tapTable;
+  int tapItemWords, tapUse;
   // backward instantiation (BWD): `vol` is the upstream gradient of the volume (read), gradFeat the zero-initialised
   // gradient image with the element layout of `feat` that the sampler's adjoint accumulates into
   float* gradFeat;
@@ -269,6 +273,22 @@ template <> struct VolT<true> { typedef uint16_t type; };
 // The record stride is odd, so the 8 records a warp reads at a time sit in 8 different banks.
 __host__ __device__ constexpr int entry_words(int cam) { return (2 + 3 * cam) | 1; }
 
+MVSGI_DEV uint32_t smem_addr32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+MVSGI_DEV void mbar_wait32(uint32_t mb, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(mb), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 MVSGI_DEV unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -310,6 +330,18 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   const int tid = threadIdx.x, lane = tid & 31, q = lane & 3;
   const int warp = tid >> 5;
   constexpr int nwarps = NT >> 5;
+  // Tap table kept across calls (MvsgiSweepArgs.tap_table, USE): an item's records arrive by one bulk asynchronous copy
+  // (cp.async.bulk global -> shared) that completes this mbarrier; its phase flips once per item.
+  __shared__ __align__(8) unsigned long long tapBar;
+  const bool tapUse = !BWD && kp.tapTable != nullptr && kp.tapUse != 0;
+  uint32_t tapPhase = 0;
+  if (tapUse) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr32(&tapBar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   const int cLane = q * 4;                       // first of the 4 channels (inside a 16-channel group) this lane owns
   const int HW = kp.Ho * kp.Wo;
   const int cs = kp.Dvol * HW;                   // channel stride of vol (host checks Cout * cs < 2^31)
@@ -353,7 +385,7 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
     const int ngroups = (npx + kp.grpPx - 1) / kp.grpPx;
     const int gsz = 8 * ((((npx + 7) >> 3) + ngroups - 1) / ngroups);
 
-    if (kp.gridMode == MVSGI_GRID_PROJECT) {
+    if (kp.gridMode == MVSGI_GRID_PROJECT && !tapUse) {
       for (int p = tid; p < npx; p += NT) {
         const int pix = min(pixel_of(p), kp.P - 1);
         float rx, ry, rz;
@@ -443,12 +475,34 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         if (!kp.perFrameMasks) vb8[(size_t)j * ES * 4 + 1 - 2 * (b & 1)] = (unsigned char)v;  // shared masks: both parities
       }
     };
-    if (!kp.perFrameGrids) {
+    if (tapUse) {
+      // the records of this item as an earlier launch built them (host: shared grids, static masks).  Every thread has
+      // passed the barrier that ends the previous item, so the table is free; the proxy fence orders those generic
+      // reads before the asynchronous write.
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(((npairs * ES + 3) >> 2) << 4);
+        const uint32_t mb = smem_addr32(&tapBar);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr32(tab)),
+                     "l"(kp.tapTable + (size_t)item * kp.tapItemWords), "r"(bytes), "r"(mb)
+                     : "memory");
+      }
+      mbar_wait32(smem_addr32(&tapBar), tapPhase);
+      tapPhase ^= 1u;
+    } else if (!kp.perFrameGrids) {
       build(0);
       __syncthreads();
       if (AGG == MVSGI_AGG_STD) {  // frame 0 (and, when masks are shared, every frame: both parity bytes at once)
         lookup_masks(0);
         __syncthreads();
+      }
+      if (!BWD && kp.tapTable != nullptr) {  // BUILD: keep the finished records for later launches
+        const uint4* src = reinterpret_cast<const uint4*>(tab);
+        uint4* dst = reinterpret_cast<uint4*>(kp.tapTable + (size_t)item * kp.tapItemWords);
+        const int n16 = (npairs * ES + 3) >> 2;
+        for (int i = tid; i < n16; i += NT) dst[i] = src[i];
       }
     }
 

@@ -86,7 +86,14 @@ class _SweepBase(nn.Module):
         # rest get less work.  A dozen extra sweep launches at the first call with a given shape.
         self.calibrate_runs = True
         self.balance_report = None
-        self._order_cache = None  # (key, int32 [runs, units] table or None)
+        self._order_cache = None  # (key, int32 [runs, units] table or None, uint8 tap table or None)
+        # Tap tables kept across calls (ops.build_tap_table, MvsgiSweepArgs.tap_table): with an attached rig and static
+        # masks the kernel's (output offset, validity, tap offsets, bilinear fractions) records are the same at every
+        # forward — what the grids the reference's dataset precomputes once per rig are to its sweep — so they are
+        # built at the first call with a given shape and copied in (one cp.async.bulk per work item) afterwards.
+        # Same volume bit for bit; pays when the batch does not amortise the build (single frames, high-D).
+        # Costs records x (12 * cams + 12) bytes of device memory (G16V 18 MB, 64 candidates at 160x640: 288 MB).
+        self.keep_tap_table = True
         # Memory layout of the volume the sweep kernel writes.  False = the reference's NCDHW.  True = the same
         # [B,C,D,Ho,Wo] tensor with torch.channels_last_3d strides: the kernel then stores 512 contiguous bytes per
         # warp and post_vol's Conv3d runs cuDNN's NDHWC path on it.  Values are identical.
@@ -185,35 +192,43 @@ class _SweepBase(nn.Module):
                 raise RuntimeError("the std builder needs masks")
             if masks.is_cuda and masks.dim() == 5 and masks.dtype in (torch.float32, torch.bool, torch.uint8):
                 masks, (mask_h, mask_w) = self._packed_masks(masks, check=self.check_masks)
-        order = None
-        if (self.balance_runs and self._rig_blob is not None and not want_valid and feats.is_cuda and
-                (masks is None or (self._static_masks is not None and masks.dtype == torch.int32))):
-            order = self._octet_order(feats, masks, mask_h, mask_w, int(Ho), int(Wo), int(D))
+        order = table = None
+        if ((self.balance_runs or self.keep_tap_table) and self._rig_blob is not None and not want_valid and
+                feats.is_cuda and (masks is None or (self._static_masks is not None and masks.dtype == torch.int32))):
+            order, table = self._octet_order(feats, masks, mask_h, mask_w, int(Ho), int(Wo), int(D))
         return ops.sweep_op(feats, grids, grid_masks, masks, self._rig_blob, self._aggregate, int(Ho), int(Wo), int(D),
                             want_valid, self.vol_channels_last, self.feats_bf16, mask_h, mask_w,
-                            self.vol_bf16 and not want_valid, order)
+                            self.vol_bf16 and not want_valid, order, table)
 
     def _octet_order(self, feats: Tensor, bits: Optional[Tensor], mask_h: int, mask_w: int, Ho: int, Wo: int, D: int):
         """Cost-balanced assignment of the output image's octets to the sweep's CTAs (ops.balanced_octet_order) for
         the attached rig and the static masks: computed at the first call with a given shape (one device
         synchronisation, skipped while a CUDA graph is being captured) and kept, like the packed masks."""
         key = (tuple(feats.shape), tuple(feats.stride()), None if bits is None else (bits.data_ptr(), bits._version),
-               mask_h, mask_w, Ho, Wo, D, self.vol_channels_last, self.feats_bf16, self.vol_bf16, feats.device)
+               mask_h, mask_w, Ho, Wo, D, self.vol_channels_last, self.feats_bf16, self.vol_bf16, feats.device,
+               self.balance_runs, self.calibrate_runs, self.keep_tap_table)
         c = self._order_cache
         if c is not None and c[0] == key:
-            return c[1]
+            return c[1], c[2]
         if torch.cuda.is_current_stream_capturing():
-            return None
+            return None, None
+        need_run = (self.balance_runs and self.calibrate_runs) or self.keep_tap_table
         call = ops.SweepCall(feats, None, None, bits, self._rig_blob, self._aggregate, Ho, Wo, D,
-                             describe_only=not self.calibrate_runs, channels_last=self.vol_channels_last,
+                             describe_only=not need_run, channels_last=self.vol_channels_last,
                              feats_bf16=self.feats_bf16, mask_hw=(mask_h, mask_w) if mask_h > 0 else None,
                              vol_bf16=self.vol_bf16)
-        if self.calibrate_runs:
-            order, self.balance_report = ops.calibrated_octet_order(call)
-        else:
-            order = ops.balanced_octet_order(call)
-        self._order_cache = (key, order)
-        return order
+        order = None
+        if self.balance_runs:
+            if self.calibrate_runs:
+                order, self.balance_report = ops.calibrated_octet_order(call)
+            else:
+                order = ops.balanced_octet_order(call)
+        table = None
+        if self.keep_tap_table:
+            call.set_octet_order(order)
+            table = ops.build_tap_table(call)  # follows the work assignment: built after it
+        self._order_cache = (key, order, table)
+        return order, table
 
 
 class SphericalSweepStdMasked(_SweepBase):

@@ -237,6 +237,26 @@ class SweepCall:
         a.octet_order, a.order_runs, a.order_units = order.data_ptr(), order.shape[0], order.shape[1]
         self.keep.append(order)
 
+    def tap_table_bytes(self) -> int:
+        """Bytes of the tap table this problem keeps across calls (mvsgi_sweep_tap_table_bytes); 0 = none (per-frame
+        grids or per-frame masks)."""
+        n = int(self.lib.mvsgi_sweep_tap_table_bytes(C.byref(self.args)))
+        if n < 0:
+            abi.check(n, "mvsgi_sweep_tap_table_bytes")
+        return n
+
+    def set_tap_table(self, table: Optional[Tensor], mode: int = abi.TAP_TABLE_USE) -> None:
+        """Attach (or, with None, detach) the uint8 buffer of `build_tap_table()` (MvsgiSweepArgs.tap_table)."""
+        a = self.args
+        if table is None:
+            a.tap_table, a.tap_table_bytes, a.tap_table_mode = None, 0, abi.TAP_TABLE_OFF
+            return
+        _require_cuda(table, "tap_table")
+        if table.dtype != torch.uint8 or table.dim() != 1 or not table.is_contiguous():
+            raise RuntimeError("tap_table must be the contiguous uint8 buffer of build_tap_table()")
+        a.tap_table, a.tap_table_bytes, a.tap_table_mode = table.data_ptr(), table.numel(), mode
+        self.keep.append(table)
+
     def launch_count(self, flags: int = 0) -> int:
         self.args.flags = flags | self.base_flags
         n = self.lib.mvsgi_sweep_launch_count(C.byref(self.args))
@@ -282,6 +302,26 @@ def lpt_assign(cost, runs: int, units: int, slowdown=None):
         load[light] += cost[chunk] * slow[light]
     # compact: empty slots (only possible in the last, partial round) stay at the end of their run by construction
     return order
+
+
+def build_tap_table(call: "SweepCall") -> Optional[Tensor]:
+    """The sweep kernel's tap tables for the problem `call` describes, kept for later calls (MvsgiSweepArgs.tap_table):
+    one sweep of `call` in BUILD mode (stages / packs what the call needs, builds the records as usual and stores them),
+    after which `call` — and every call with the same shapes, strides, masks, rig and octet_order — copies them in with
+    one bulk asynchronous copy per work item instead of evaluating the geometry.  The role of the grids the reference
+    precomputes once per rig (multi_view_camera_model_dataset.py:519-557).  Attach `octet_order` first: the table
+    follows the work assignment.  -> uint8 buffer (attached to `call` in USE mode), or None when the problem keeps no
+    table (per-frame grids / masks)."""
+    n = call.tap_table_bytes()
+    if n <= 0:
+        return None
+    # zero-filled: slots of items with fewer records than the largest are copied whole-sale up to their own length only,
+    # but a defined buffer keeps compute-sanitizer's initcheck quiet
+    table = torch.zeros((n,), dtype=torch.uint8, device=call.device)
+    call.set_tap_table(table, abi.TAP_TABLE_BUILD)
+    call.run()
+    call.set_tap_table(table, abi.TAP_TABLE_USE)
+    return table
 
 
 def balanced_octet_order(call: "SweepCall") -> Optional[Tensor]:
@@ -396,10 +436,13 @@ def calibrated_octet_order(call: "SweepCall", rounds: int = 3, threshold: float 
 
 
 def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                channels_last=False, feats_bf16=False, mask_h=0, mask_w=0, vol_bf16=False, octet_order=None):
+                channels_last=False, feats_bf16=False, mask_h=0, mask_w=0, vol_bf16=False, octet_order=None,
+                tap_table=None):
     call = SweepCall(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
                      channels_last=channels_last, feats_bf16=feats_bf16,
                      mask_hw=(mask_h, mask_w) if mask_h > 0 else None, vol_bf16=vol_bf16, octet_order=octet_order)
+    if tap_table is not None:
+        call.set_tap_table(tap_table, abi.TAP_TABLE_USE)
     call.run()
     # inputs and workspace are only read by kernels already enqueued on this stream; the caching allocator reuses
     # freed blocks in stream order, so dropping the references here is safe.
@@ -410,16 +453,18 @@ def _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out
 def sweep_op(feats: Tensor, grids: Optional[Tensor], grid_masks: Optional[Tensor], masks: Optional[Tensor],
              rig_blob: Optional[Tensor], aggregate: int, out_h: int, out_w: int, num_cands: int,
              want_valid: bool, channels_last: bool = False, feats_bf16: bool = False, mask_h: int = 0,
-             mask_w: int = 0, vol_bf16: bool = False, octet_order: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+             mask_w: int = 0, vol_bf16: bool = False, octet_order: Optional[Tensor] = None,
+             tap_table: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """`masks`: [B|1, CAM, 1, Hm, Wm] float32 / bool / uint8 (reference interface), or the int32 bits of pack_masks()
-    with mask_h, mask_w = the size of the masks they were packed from.  `octet_order`: balanced_octet_order()."""
+    with mask_h, mask_w = the size of the masks they were packed from.  `octet_order`: balanced_octet_order().
+    `tap_table`: build_tap_table() of a call with exactly these shapes, strides, masks, rig and octet_order."""
     return _sweep_impl(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid,
-                       channels_last, feats_bf16, mask_h, mask_w, vol_bf16, octet_order)
+                       channels_last, feats_bf16, mask_h, mask_w, vol_bf16, octet_order, tap_table)
 
 
 @sweep_op.register_fake
 def _(feats, grids, grid_masks, masks, rig_blob, aggregate, out_h, out_w, num_cands, want_valid, channels_last=False,
-      feats_bf16=False, mask_h=0, mask_w=0, vol_bf16=False, octet_order=None):
+      feats_bf16=False, mask_h=0, mask_w=0, vol_bf16=False, octet_order=None, tap_table=None):
     B, CAM, Cc = feats.shape[:3]
     cout = Cc if aggregate == abi.AGG_STD else CAM * Cc
     vol = torch.empty((B, cout, num_cands, out_h, out_w), dtype=torch.bfloat16 if vol_bf16 else feats.dtype,
@@ -529,7 +574,7 @@ def _sweep_bwd(ctx, grad_vol, grad_valid):
     if ctx.needs_input_grad[0] and grad_vol is not None:
         grad_vol = grad_vol.float()  # a bfloat16 volume (vol_bf16) hands back a bfloat16 gradient
         gf = sweep_backward_op(grad_vol, feats, grids, grid_masks, masks, rig_blob, *ctx.meta)
-    return gf, None, None, None, None, None, None, None, None, None, None, None, None, None, None, None
+    return (gf,) + (None,) * 16
 
 
 sweep_op.register_autograd(_sweep_bwd, setup_context=_sweep_setup)
