@@ -204,6 +204,10 @@ class CandidateShardedSweep(torch.nn.Module):
         self.fused = fused
         self._peer_volume: Optional[PeerVolume] = None
         self._flag: Optional[Tensor] = None
+        # fused path: the sweep kernel's tap tables of this rank's candidate slice are kept across calls
+        # (ops.build_tap_table — the first call with a given shape / masks tensor is the BUILD launch)
+        self.keep_tap_table = True
+        self._tap_cache = None  # (key, uint8 table or None)
         self.full_rig = rig
         self.num_cands = rig.num_cands if rig is not None else None
         if rig is not None:
@@ -257,11 +261,27 @@ class CandidateShardedSweep(torch.nn.Module):
         vol, peers = self._peer_volume.next()
         if cl:
             vol = vol.permute(0, 4, 1, 2, 3)
-        if std and b._static_masks is not None:
-            masks = b._static_masks
+        mask_hw = None
+        if std and b._static_masks is not None:  # the module's packed bits: no packing kernel per call
+            masks, mask_hw = b._packed_masks(b._static_masks, check=False)
         call = ops.SweepCall(feats, g, gm, masks if std else None, b._rig_blob, b._aggregate, Ho, Wo, d1 - d0,
-                             out=vol, cand_offset=d0, peer_ptrs=peers, channels_last=cl)
-        call.run()
+                             out=vol, cand_offset=d0, peer_ptrs=peers, channels_last=cl, mask_hw=mask_hw)
+        ran = False
+        if self.keep_tap_table and g is None and not torch.cuda.is_current_stream_capturing():
+            m = masks if std else None
+            key = (tuple(feats.shape), tuple(feats.stride()), None if m is None else (m.data_ptr(), m._version, mask_hw),
+                   shape, d0, d1, feats.device)
+            c = self._tap_cache
+            if c is not None and c[0] == key:
+                if c[1] is not None:
+                    call.set_tap_table(c[1])
+            else:
+                # BUILD is a complete sweep of this call (peer stores included) that also keeps its records
+                table = ops.build_tap_table(call)
+                self._tap_cache = (key, table)
+                ran = table is not None
+        if not ran:
+            call.run()
         if world > 1:
             # stream-ordered rendezvous: it starts after this rank's sweep kernel and ends when every rank has joined,
             # i.e. when every rank's stores into this volume have been issued and their kernels have completed
