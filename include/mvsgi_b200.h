@@ -221,7 +221,9 @@ typedef struct MvsgiSweepArgs {
    *                          asynchronous copy (cp.async.bulk + mbarrier) instead of evaluating the geometry.
    * A table is valid for calls whose arguments equal the BUILD call's except feats / vol / workspace pointer VALUES
    * (same strides, masks contents, rig, octet_order contents, batch); the volume is bit-identical to MVSGI_TAP_TABLE_OFF.
-   * Pays when the batch does not amortise the build: high-D (64 candidates, 160x640, 2 frames) 0.73 -> see DESIGN §6. */
+   * Pays when the batch does not amortise the build (profiles/r4a_tap_table.jsonl): one G16V frame 35 -> 19 us, 64
+   * candidates at 160x640 x 2 frames 0.71 -> 0.49 ms, 32 G16V frames 0.359 -> 0.341 ms.  Size: 4 * ((2 + 3 * cams) | 1) bytes per
+   * (candidate, pixel) record (44 at 3 cameras) — 18 MB at G16V, 288 MB at high-D; ask mvsgi_sweep_tap_table_bytes. */
   void* tap_table;
   int64_t tap_table_bytes;
   int32_t tap_table_mode; /* MVSGI_TAP_TABLE_* */
