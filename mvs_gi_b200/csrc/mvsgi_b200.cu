@@ -436,6 +436,7 @@ void fill_kp(const MvsgiSweepArgs* a, const SweepPlan& p, float* ws_feats, uint3
   kp.tapTable = a->tap_table_mode != MVSGI_TAP_TABLE_OFF ? reinterpret_cast<uint32_t*>(a->tap_table) : nullptr;
   kp.tapItemWords = (int)p.tap_item_words;
   kp.tapUse = a->tap_table_mode == MVSGI_TAP_TABLE_USE ? 1 : 0;
+  kp.itemQueue = nullptr;  // set by mvsgi_sweep_f32 (the counter lives in the call's workspace)
   kp.wL = p.walk ? p.w_len : 0; kp.wSegs = p.walk ? p.w_segs : 0; kp.wNumSeg = p.walk ? p.w_num_seg : 0;
   if (p.direct) {  // the caller's channels-last tensor: element (b, cam, y, x, c) at b*s0 + cam*s1 + y*s3 + x*s4 + c
     kp.feat = a->feats;
@@ -792,6 +793,13 @@ int mvsgi_sweep_f32(const MvsgiSweepArgs* a, void* stream) {
     return (int)e;
   }
 #endif
+  // kept tap table and several items per CTA: the items after the first are drawn from a queue (sweep.cuh); its counter
+  // is 4 bytes of the call's workspace, zeroed on the stream (a memset node when captured into a CUDA graph)
+  if (a->tap_table_mode == MVSGI_TAP_TABLE_USE && p.num_items > p.grid && !p.oct_order) {
+    kp.itemQueue = ws_flags + 32;
+    e = cudaMemsetAsync(kp.itemQueue, 0, sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+  }
   e = mvsgi::launch_sweep_cta(a->aggregate, a->num_cams, kp, rig, p.grid, p.smem_bytes, st);
   g_launches++;
   return (int)e;

@@ -70,6 +70,7 @@ struct SweepKP {
   // instead of built, 0: built and stored; nullptr = not kept
   uint32_t* tapTable;
   int tapItemWords, tapUse;
+  int* itemQueue;  // USE with more items than CTAs: zeroed counter (workspace) the CTAs draw their later items from
   // backward instantiation (BWD): `vol` is the upstream gradient of the volume (read), gradFeat the zero-initialised
   // gradient image with the element layout of `feat` that the sampler's adjoint accumulates into
   float* gradFeat;
@@ -347,8 +348,18 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
   const int cs = kp.Dvol * HW;                   // channel stride of vol (host checks Cout * cs < 2^31)
   const int numOct = (kp.P + 7) >> 3;            // runs and locality groups are made of 8-pixel octets (32-byte sectors)
 
-  for (int item = blockIdx.x; item < kp.numItems; item += gridDim.x) {
-    const int run = item / kp.numChunks, chunk = item - run * kp.numChunks;
+  // Items: CTA c takes items c, c + grid, ...; with a kept tap table (USE) and more items than CTAs the items after a CTA's
+  // first come from a queue (one atomicAdd per item, issued by thread 0 when the previous item starts so that its latency
+  // is hidden): the CTAs of the high-D sweep, 16 items each, ended between 296 and 488 us with the static deal
+  // (profiles/r4e_cta_times_highd.txt) — any order of the items gives the same volume.
+  __shared__ int nextItem;
+  const bool dynItems = tapUse && kp.itemQueue != nullptr;
+  // Candidate chunk of an item: rotated by the item's wave, because grid % numChunks == 0 would otherwise hand CTA c the
+  // same chunk (c % numChunks) in every wave, and the chunks differ in cost (near candidates sample fewer cameras).
+  const int chunkRot = kp.numChunks > 1 ? max(1, (int)gridDim.x / kp.numChunks) : 1;
+  for (int item = blockIdx.x; item < kp.numItems;) {
+    const int run = item / kp.numChunks;
+    const int chunk = kp.numChunks > 1 ? (item - run * kp.numChunks + run / chunkRot) % kp.numChunks : 0;
     // A run is either a contiguous range of octets or (interleave) every numRuns-th octet: the strided form spreads
     // the expensive image regions (all cameras valid) and the cheap ones (masked out) evenly over the CTAs.
     int p0, npx;
@@ -488,6 +499,15 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
                          smem_addr32(tab)),
                      "l"(kp.tapTable + (size_t)item * kp.tapItemWords), "r"(bytes), "r"(mb)
                      : "memory");
+        // the item after this one, drawn while the copy travels.  Every thread has read the previous nextItem before the
+        // barrier above; the barrier that ends this item's last pass publishes the new one.
+        if (dynItems) nextItem = (int)gridDim.x + atomicAdd(kp.itemQueue, 1);
+        // ... and its table asked into L2 now, so that the copy at its start is an L2 hit rather than a DRAM round trip
+        const int nxt = dynItems ? nextItem : item + (int)gridDim.x;
+        if (nxt < kp.numItems)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kp.tapTable + (size_t)nxt * kp.tapItemWords),
+                       "r"((uint32_t)kp.tapItemWords * 4u)
+                       : "memory");
       }
       mbar_wait32(smem_addr32(&tapBar), tapPhase);
       tapPhase ^= 1u;
@@ -763,7 +783,9 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
       // warps cost +30 % L2->L1 traffic).
       __syncthreads();
     }
-    // (the barrier above also protects the table: the next item's build overwrites it)
+    // (the barrier above also protects the table: the next item's build overwrites it; it also publishes nextItem,
+    // which thread 0 rewrites only after the first barrier of the item that follows)
+    item = dynItems ? nextItem : item + (int)gridDim.x;
   }
   if (kp.ctaTimes != nullptr && threadIdx.x == 0) kp.ctaTimes[4 * blockIdx.x + 3] = gtimer();
 }

@@ -65,7 +65,8 @@ def _inputs(dev, name, B, kw, seed=5, nhwc=True):
     ("G16V", 17, {}, True, True, True),       # 4 frames per pass
     ("G16V", 2, {}, False, False, False),     # the reference layouts: NCHW features (staged), NCDHW volume
     ("4CAM", 6, {}, True, True, True),        # two waves of runs per CTA: the mbarrier phase flips between items
-    ("HIGHD", 2, {}, False, True, True),      # 64 candidates in chunks of 16: 16 items per CTA
+    ("4CAM", 6, {}, False, True, True),       # ... without the table of runs: the later items come from the queue
+    ("HIGHD", 2, {}, False, True, True),      # 64 candidates in chunks of 16: 16 items per CTA, drawn from the queue
     ("G8", 3, {}, True, True, True),          # concat builder
     ("G16V_DS", 2, {}, False, True, True),    # DoubleSphere projection
     ("G16VV_C48", 2, {}, False, True, True),  # three channel groups
@@ -182,3 +183,29 @@ def test_module_builds_the_tap_table_once_and_reuses_it(dev):
     f = feats[0].clone().requires_grad_(True)
     kept.sweep(f, None, None, None).sum().backward()
     assert f.grad is not None and torch.isfinite(f.grad).all()
+
+
+@pytest.mark.gpu
+def test_item_queue_of_a_kept_table_replays_from_a_cuda_graph(dev):
+    """More items than CTAs + a kept table: the CTAs draw their later items from a counter in the call's workspace that
+    mvsgi_sweep_f32 zeroes on the stream (a memset node in a captured graph) — every replay sweeps every item once."""
+    from mvs_gi_b200 import ops
+
+    w, feats, mk = _inputs(dev, "HIGHD", 1, {})
+    plain, kept = mk(), mk()
+    plain.run()
+    ops.build_tap_table(kept)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        kept.run()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        kept.run()
+    for _ in range(3):
+        kept.vol.fill_(float("nan"))
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(plain.vol.view(torch.int32), kept.vol.view(torch.int32))
