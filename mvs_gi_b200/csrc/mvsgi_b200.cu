@@ -263,6 +263,12 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
                (a->flags & MVSGI_FLAG_VOL_CHANNELS_LAST) && a->valid_out == nullptr && a->num_peers == 0 &&
                env_int("MVSGI_FB_ON", 1) != 0)
                   ? mvsgi::sweep_frames_per_pass(a->num_cams, a->batch, p->cg) : 1;
+  // Kept tap table (USE): there is no table build for the fewer, fatter threads of the wide variant to be slow at, so it
+  // pays from 4 (4 cameras: 3) frames on instead of 16 (6).  The table's layout does not depend on the variant.
+  if (a->tap_table_mode == MVSGI_TAP_TABLE_USE && p->cta_fb == 2 && p->cg == 1) {
+    if (a->num_cams <= 3 && a->batch >= 4) p->cta_fb = 4;
+    else if (a->num_cams == 4 && a->batch >= 3) p->cta_fb = 3;
+  }
   const int max_ctas = mvsgi::sweep_ctas(p->cta_fb);
   int ctas_per_sm = env_int("MVSGI_CTAS_PER_SM", max_ctas);
   if (ctas_per_sm < 1) ctas_per_sm = 1;

@@ -502,12 +502,8 @@ sweep_kernel(const SweepKP kp, const __grid_constant__ MvsgiRig rig) {
         // the item after this one, drawn while the copy travels.  Every thread has read the previous nextItem before the
         // barrier above; the barrier that ends this item's last pass publishes the new one.
         if (dynItems) nextItem = (int)gridDim.x + atomicAdd(kp.itemQueue, 1);
-        // ... and its table asked into L2 now, so that the copy at its start is an L2 hit rather than a DRAM round trip
-        const int nxt = dynItems ? nextItem : item + (int)gridDim.x;
-        if (nxt < kp.numItems)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kp.tapTable + (size_t)nxt * kp.tapItemWords),
-                       "r"((uint32_t)kp.tapItemWords * 4u)
-                       : "memory");
+        // (asking the next item's table into L2 here — cp.async.bulk.prefetch.L2 — measured slower: high-D 0.434 ->
+        // 0.451 ms, profiles/r4g_prefetch_fb.jsonl; the 18 MB of prefetched tables compete with the taps for L2)
       }
       mbar_wait32(smem_addr32(&tapBar), tapPhase);
       tapPhase ^= 1u;
