@@ -35,7 +35,8 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_structs_match_the_c_layout(tmp_path):
     structs = ["MvsgiCamera", "MvsgiRig", "MvsgiSweepArgs", "MvsgiProjectArgs", "MvsgiSoftArgminArgs",
                "MvsgiResampleArgs"]
-    probes = {"MvsgiSweepArgs": ["feats", "masks", "grids", "rig", "vol", "workspace", "cand_offset", "peer_vols"],
+    probes = {"MvsgiSweepArgs": ["feats", "masks", "grids", "rig", "vol", "workspace", "cand_offset", "peer_vols", "octet_order",
+                                 "cta_times_out", "tap_table", "tap_table_bytes", "tap_table_mode"],
               "MvsgiSoftArgminArgs": ["costs", "inv_dist_idx", "argmax"], "MvsgiRig": ["cams", "dist"],
               "MvsgiCamera": ["rot", "p"], "MvsgiProjectArgs": ["rig", "grid_masks"],
               "MvsgiResampleArgs": ["img", "img_stride", "rig", "invalid_value", "out", "valid_out"]}

@@ -21,6 +21,44 @@ def test_sweep_args_carry_the_tap_table_fields():
     assert "mvsgi_sweep_tap_table_bytes" in abi.EXPORTS
 
 
+def test_tap_table_size_is_planned_without_a_gpu():
+    """mvsgi_sweep_tap_table_bytes only plans: G16V keeps 44-byte records for 25 600 pixels x 16 candidates in 296
+    slots (18.3 MB), per-frame masks keep nothing, and a launch that asks for a table it cannot keep is refused before
+    anything is enqueued."""
+    from mvs_gi_b200 import abi, synthetic
+
+    lib = abi.load_library()
+    w = synthetic.WORKLOADS["G16V"]
+    rig = w.rig().to_struct()
+    a = abi.MvsgiSweepArgs()
+    a.struct_size = C.sizeof(a)
+    a.aggregate, a.grid_mode, a.flags = abi.AGG_STD, abi.GRID_PROJECT, abi.FLAG_VOL_CHANNELS_LAST
+    a.batch, a.num_cams, a.feat_chs, a.num_cands = 32, w.num_cams, w.feat_chs, len(w.dist_list)
+    a.feat_h, a.feat_w = w.feat_hw
+    a.out_h, a.out_w = w.cv_hw
+    a.mask_h, a.mask_w = w.mask_hw
+    Hf, Wf, Cc = w.feat_hw[0], w.feat_hw[1], w.feat_chs
+    a.feats = 1 << 20  # never dereferenced by the planner
+    for i, st in enumerate((w.num_cams * Hf * Wf * Cc, Hf * Wf * Cc, 1, Wf * Cc, Cc)):  # channels-last
+        a.feats_stride[i] = st
+    a.masks, a.masks_dtype = 1 << 20, abi.MASK_PACKED
+    words = (w.mask_hw[0] + 2) * lib.mvsgi_mask_pitch_words(w.mask_hw[1]) * 2
+    a.masks_stride[0], a.masks_stride[1] = 0, words
+    a.rig = C.pointer(rig)
+    need = lib.mvsgi_sweep_tap_table_bytes(C.byref(a))
+    pairs = w.cv_hw[0] * w.cv_hw[1] * len(w.dist_list)
+    assert need % 256 == 0 and pairs * 44 <= need <= int(pairs * 44 * 1.15), need
+    # per-frame masks: the validity bits of the records change with the frame
+    a.masks_stride[0] = w.num_cams * words
+    assert lib.mvsgi_sweep_tap_table_bytes(C.byref(a)) == 0
+    a.vol, a.tap_table, a.tap_table_bytes, a.tap_table_mode = 1 << 20, 1 << 20, need, abi.TAP_TABLE_USE
+    assert lib.mvsgi_sweep_launch_count(C.byref(a)) == abi.E_UNSUPPORTED
+    a.masks_stride[0] = 0
+    assert lib.mvsgi_sweep_launch_count(C.byref(a)) >= 1
+    a.tap_table_bytes = need - 1
+    assert lib.mvsgi_sweep_launch_count(C.byref(a)) < 0
+
+
 # ------------------------------------------------------------------------------------------------- GPU
 @pytest.fixture(scope="module")
 def dev():
