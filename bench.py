@@ -232,6 +232,7 @@ def run_reference(args, w):
                 "masks": "per_frame", "feats_layout": "nchw", "vol_layout": "ncdhw", "norm_costs": True,
                 "parallelism": "rank 0 only", "cache": "same inputs every step",
                 "runs": "n/a (the reference formulation: a python loop over candidates of ATen ops)",
+                "tap_table": "n/a (the reference reads its precomputed grids at every call)",
                 "device": "cuda:0" if on_gpu else "cpu"})
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
