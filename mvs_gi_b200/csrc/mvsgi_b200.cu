@@ -265,9 +265,22 @@ int validate_and_plan(const MvsgiSweepArgs* a, SweepPlan* p) {
                   ? mvsgi::sweep_frames_per_pass(a->num_cams, a->batch, p->cg) : 1;
   // Kept tap table (USE): there is no table build for the fewer, fatter threads of the wide variant to be slow at, so it
   // pays from 4 (4 cameras: 3) frames on instead of 16 (6).  The table's layout does not depend on the variant.
-  if (a->tap_table_mode == MVSGI_TAP_TABLE_USE && p->cta_fb == 2 && p->cg == 1) {
-    if (a->num_cams <= 3 && a->batch >= 4) p->cta_fb = 4;
-    else if (a->num_cams == 4 && a->batch >= 3) p->cta_fb = 3;
+  // Below 16 frames the variant is picked by cost: passes x frames per pass (a batch that is not a multiple re-sweeps the
+  // frames its last pass shares with the one before) x the measured relative cost of a frame in that variant
+  // (profiles/r4g_prefetch_fb.jsonl, profiles/r4n_small_batch_fb1.jsonl: wide 1.00, two frames 1.10, one frame 1.17).
+  if (a->tap_table_mode == MVSGI_TAP_TABLE_USE && p->cta_fb >= 2 && a->batch < 16) {
+    const int fbs[3] = {p->cg == 1 ? (a->num_cams == 4 ? 3 : 4) : 0, 2, 1};
+    const double rel[3] = {1.00, 1.10, 1.17};
+    double best = 1e30;
+    for (int i = 0; i < 3; ++i) {
+      const int fb = fbs[i];
+      if (fb < 1 || fb > a->batch) continue;
+      const double cost = (double)((a->batch + fb - 1) / fb) * fb * rel[i];
+      if (cost < best - 1e-9) {
+        best = cost;
+        p->cta_fb = fb;
+      }
+    }
   }
   const int max_ctas = mvsgi::sweep_ctas(p->cta_fb);
   int ctas_per_sm = env_int("MVSGI_CTAS_PER_SM", max_ctas);

@@ -99,8 +99,11 @@ def _inputs(dev, name, B, kw, seed=5, nhwc=True):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,B,kw,balanced,nhwc,cl", [
     ("G16V", 1, {}, False, True, True),       # one frame per pass
-    ("G16V", 5, {}, True, True, True),        # 2 frames per pass, ragged last pass, cost-balanced runs
+    ("G16V", 5, {}, True, True, True),        # BUILD 2 frames per pass (ragged last pass), USE 1 frame per pass; balanced runs
     ("G16V", 17, {}, True, True, True),       # 4 frames per pass
+    ("G16V", 7, {}, False, True, True),       # kept table: 4 frames per pass from 4 frames on, ragged last pass
+    ("G16V", 6, {}, False, True, True),       # ... 2 frames per pass where that re-sweeps fewer frames
+    ("4CAM", 4, {}, False, True, True),
     ("G16V", 2, {}, False, False, False),     # the reference layouts: NCHW features (staged), NCDHW volume
     ("4CAM", 6, {}, True, True, True),        # two waves of runs per CTA: the mbarrier phase flips between items
     ("4CAM", 6, {}, False, True, True),       # ... without the table of runs: the later items come from the queue
